@@ -1,0 +1,265 @@
+// HBM-/latency-bound glue kernels of the denoise step (sm_100a): layout seams, samplers' data movement,
+// timestep embeddings, skinny (M <= 16) linears, and the fused CFG + DDPM update.
+// Reference call sites are cited per kernel; rounding points follow the fp16-autocast path.
+#include "common.cuh"
+#include "host.h"
+
+namespace vton {
+
+// ------------------------------------------------------------------------------------------------
+// NCHW <-> NHWC seams. The reference's UNet API is NCHW (src/unet_hacked_tryon.py:1006); the engine is NHWC.
+// scatter: dst[s, y, x, c_off + c] = src[s % Bs, c, y, x]   (CFG duplication `torch.cat([latents]*2)`,
+//          src/tryon_pipeline.py:1769, and the 13-channel concat, :1777, become channel offsets)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const __half* src, int Bs, int Cs, int HW, __half* dst, int Bd, int ldc, int c_off) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Bd) * HW;
+  if (i >= total) return;
+  const int s = static_cast<int>(i / HW);
+  const int px = static_cast<int>(i % HW);
+  const int sb = s % Bs;
+  for (int c = 0; c < Cs; ++c) dst[i * ldc + c_off + c] = src[(static_cast<long long>(sb) * Cs + c) * HW + px];
+}
+
+__global__ void nhwc_to_nchw_kernel(const __half* src, int B, int C, int HW, int ldc, __half* dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (i >= total) return;
+  const int px = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+  dst[i] = src[(static_cast<long long>(b) * HW + px) * ldc + c];
+}
+
+int nchw_to_nhwc_impl(const void* src, int Bs, int Cs, int H, int W, void* dst, int Bd, int ldc, int c_off,
+                      cudaStream_t stream) {
+  VTON_CHECK_ARG(Bs > 0 && Cs > 0 && H > 0 && W > 0 && Bd > 0 && c_off + Cs <= ldc, "nchw_to_nhwc: bad shape");
+  const long long total = static_cast<long long>(Bd) * H * W;
+  nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __half*>(src), Bs, Cs, H * W, static_cast<__half*>(dst), Bd, ldc, c_off);
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int nhwc_to_nchw_impl(const void* src, int B, int C, int H, int W, int ldc, void* dst, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && C <= ldc, "nhwc_to_nchw: bad shape");
+  const long long total = static_cast<long long>(B) * C * H * W;
+  nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __half*>(src), B, C, H * W, ldc, static_cast<__half*>(dst));
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Upsample2D data movement: nearest x2 (diffusers Upsample2D = F.interpolate(scale 2, nearest) then conv3x3;
+// built at src/unet_block_hacked_tryon.py:2301,2443). NHWC, 16-byte vectors.
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* src, int B, int H, int W, int V, uint4* dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 4 * H * W * V;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  long long t = i / V;
+  const int x = static_cast<int>(t % (2 * W));
+  t /= 2 * W;
+  const int y = static_cast<int>(t % (2 * H));
+  const int b = static_cast<int>(t / (2 * H));
+  dst[i] = src[((static_cast<long long>(b) * H + (y >> 1)) * W + (x >> 1)) * V + v];
+}
+
+int upsample2x_impl(const void* src, int B, int H, int W, int C, void* dst, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x: bad shape");
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(src), B, H, W, C / 8, static_cast<uint4*>(dst));
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Downsample2D (conv3x3 stride 2 pad 1; src/unet_block_hacked_tryon.py:1113,1246): gather the strided patches into
+// A[b*Ho*Wo, 9*C] (tap-major K) and run the plain GEMM against W[Cout, 9*C].
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_s2_kernel(const uint4* src, int B, int H, int W, int V, int Ho, int Wo, uint4* dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * V;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % V);
+  long long t = i / V;
+  const int tap = static_cast<int>(t % 9);
+  t /= 9;
+  const int ox = static_cast<int>(t % Wo);
+  t /= Wo;
+  const int oy = static_cast<int>(t % Ho);
+  const int b = static_cast<int>(t / Ho);
+  const int iy = 2 * oy + tap / 3 - 1;
+  const int ix = 2 * ox + tap % 3 - 1;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = src[((static_cast<long long>(b) * H + iy) * W + ix) * V + v];
+  dst[i] = val;
+}
+
+int im2col_s2_impl(const void* src, int B, int H, int W, int C, void* dst, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && H > 0 && W > 0 && C % 8 == 0, "im2col_s2: bad shape");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
+  im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(src), B, H, W, C / 8, Ho, Wo, static_cast<uint4*>(dst));
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sinusoidal timestep embedding (diffusers Timesteps, flip_sin_to_cos=True, freq_shift=0): out = [cos | sin],
+// fp32 math, fp16 store (`t_emb.to(dtype=sample.dtype)`, src/unet_hacked_tryon.py:1134-1139).
+// values: [n] floats on device; out: [n, dim]
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* values, int n, int dim, __half* out, int rows_repeat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half_dim = dim / 2;
+  if (i >= n * rows_repeat * half_dim) return;
+  const int k = i % half_dim;
+  const int r = i / half_dim;
+  const float t = values[r % n];
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half_dim));
+  const float arg = t * freq;
+  out[static_cast<long long>(r) * dim + k] = f2h(cosf(arg));
+  out[static_cast<long long>(r) * dim + half_dim + k] = f2h(sinf(arg));
+}
+
+int timestep_embed_impl(const void* values, int n, int dim, int rows_repeat, void* out, cudaStream_t stream) {
+  VTON_CHECK_ARG(n > 0 && dim > 0 && dim % 2 == 0 && rows_repeat > 0, "timestep_embed: bad shape");
+  const int total = n * rows_repeat * (dim / 2);
+  timestep_embed_kernel<<<(total + 127) / 128, 128, 0, stream>>>(static_cast<const float*>(values), n, dim,
+                                                                  static_cast<__half*>(out), rows_repeat);
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinny linear for the embedding MLPs (M <= 16 rows): TimestepEmbedding linear_1/linear_2, add_embedding, and all
+// per-resnet time_emb_proj batched into one call. One warp per output column; weights are read once.
+//   x' = in_silu ? fp16(silu(x)) : x ; y = fp16(W x' + b) ; y = out_silu ? fp16(silu(y)) : y ; y = addend ? fp16(y + addend) : y
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_MAXM = 16;
+
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const __half* x, int ldx, int M, int K, const __half* W, long long ldw, int N, const __half* bias,
+                     int in_silu, int out_silu, const __half* addend, int ld_add, __half* out, int ldo) {
+  extern __shared__ __half xs[];  // [M][K] activated input
+  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+    const int m = i / K, k = i % K;
+    __half v = x[static_cast<long long>(m) * ldx + k];
+    if (in_silu) v = f2h(silu_f(h2f(v)));
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float acc[SK_MAXM];
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) acc[m] = 0.f;
+  const __half* wrow = W + static_cast<long long>(n) * ldw;
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 wu = *reinterpret_cast<const uint4*>(wrow + k);
+    const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w};
+    float wf[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_h2(ww[j]);
+      wf[2 * j] = f.x;
+      wf[2 * j + 1] = f.y;
+    }
+#pragma unroll
+    for (int m = 0; m < SK_MAXM; ++m) {
+      if (m < M) {
+        const uint4 xu = *reinterpret_cast<const uint4*>(xs + m * K + k);
+        const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_h2(xw[j]);
+          acc[m] += f.x * wf[2 * j] + f.y * wf[2 * j + 1];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SK_MAXM; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+    const float b = bias ? h2f(bias[n]) : 0.f;
+    for (int m = 0; m < M; ++m) {
+      float y = round_h(acc[m] + b);
+      if (out_silu) y = round_h(silu_f(y));
+      if (addend) y = round_h(y + h2f(addend[static_cast<long long>(m) * ld_add + n]));
+      out[static_cast<long long>(m) * ldo + n] = f2h(y);
+    }
+  }
+}
+
+int skinny_linear_impl(const void* x, int ldx, int M, int K, const void* W, long long ldw, int N, const void* bias,
+                       int in_silu, int out_silu, const void* addend, int ld_add, void* out, int ldo,
+                       cudaStream_t stream) {
+  VTON_CHECK_ARG(M > 0 && M <= SK_MAXM, "skinny_linear: M=%d out of range (1..%d)", M, SK_MAXM);
+  VTON_CHECK_ARG(K % 8 == 0 && ldw % 8 == 0 && N > 0, "skinny_linear: K/ldw must be multiples of 8");
+  const size_t smem = static_cast<size_t>(M) * K * sizeof(__half);
+  VTON_CHECK_ARG(smem <= 96 * 1024, "skinny_linear: M*K too large");
+  static bool configured = false;
+  if (!configured) {
+    VTON_CUDA(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  skinny_linear_kernel<<<cdiv(N, 8), 256, smem, stream>>>(
+      static_cast<const __half*>(x), ldx, M, K, static_cast<const __half*>(W), ldw, N, static_cast<const __half*>(bias),
+      in_silu, out_silu, static_cast<const __half*>(addend), ld_add, static_cast<__half*>(out), ldo);
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused classifier-free guidance + DDPM ancestral step (src/tryon_pipeline.py:1814-1823; diffusers DDPMScheduler.step,
+// epsilon prediction, fixed_small variance). Every op rounds to fp16 like the reference's fp16 tensor arithmetic:
+//   g = u + fp16(gs * fp16(c - u));  x0 = fp16(fp16(x - fp16(sb * g)) * inv_sa);
+//   prev = fp16(fp16(c0 * x0) + fp16(c1 * x));  out = prev + fp16(sigma * noise)   (noise == null at t == 0)
+// eps: NHWC [2B, HW, ldc] (uncond rows first, then cond); latents/noise/out: NCHW [B, 4, HW]. Coefficients live on the
+// device ([6] floats: gs, sb, inv_sa, c0, c1, sigma) so a captured CUDA graph can be replayed for every step.
+// ------------------------------------------------------------------------------------------------
+__global__ void cfg_ddpm_kernel(const __half* eps, int ldc, int B, int C, int HW, const __half* latents,
+                                const __half* noise, const float* coef, int do_cfg, __half* out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (i >= total) return;
+  const int px = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+  const float gs = coef[0], sb = coef[1], inv_sa = coef[2], c0 = coef[3], c1 = coef[4], sigma = coef[5];
+  float g;
+  if (do_cfg) {
+    const float u = h2f(eps[(static_cast<long long>(b) * HW + px) * ldc + c]);
+    const float t = h2f(eps[(static_cast<long long>(b + B) * HW + px) * ldc + c]);
+    g = round_h(u + round_h(gs * round_h(t - u)));
+  } else {
+    g = h2f(eps[(static_cast<long long>(b) * HW + px) * ldc + c]);
+  }
+  const float x = h2f(latents[i]);
+  const float x0 = round_h(round_h(x - round_h(sb * g)) * inv_sa);
+  float prev = round_h(round_h(c0 * x0) + round_h(c1 * x));
+  if (noise) prev = round_h(prev + round_h(sigma * h2f(noise[i])));
+  out[i] = f2h(prev);
+}
+
+int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const void* latents, const void* noise,
+                  const void* coef, int do_cfg, void* out, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && C > 0 && C <= ldc && H > 0 && W > 0 && coef, "cfg_ddpm: bad arguments");
+  const long long total = static_cast<long long>(B) * C * H * W;
+  cfg_ddpm_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __half*>(eps), ldc, B, C, H * W, static_cast<const __half*>(latents),
+      static_cast<const __half*>(noise), static_cast<const float*>(coef), do_cfg, static_cast<__half*>(out));
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace vton

@@ -1,0 +1,474 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for the IDM-VTON UNets (sm_100a).
+//
+//   linear : out[M,N] = epi( A[M,K] . W[N,K]^T )                (K8 in SURVEY.md 2.3: to_q/k/v/out, proj_in/out, FF)
+//   conv3x3: out[b,y,x,:] = epi( sum_taps A[b,y+dy,x+dx,:] . W[tap][:, :]^T  (+ 1x1 shortcut in a 2nd accumulator) )
+//            (K1/K2/K5: ResnetBlock2D conv1/conv2/conv_shortcut, conv_in, conv_out; NHWC, pad 1, stride 1)
+//
+// One CTA computes one 128 x BN output tile. Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM
+// allocator), warps 2..5 = epilogue (TMEM -> registers -> fp16 -> global). Operands are staged by TMA into
+// 128B-swizzled shared memory, accumulators live in TMEM (fp32). The conv walks K as 9 taps x Cin/64 slabs with a 4-D
+// tensor map over [B,H,W,C]; out-of-bounds box elements are zero-filled by TMA, which is the conv's zero padding.
+// Epilogue rounding points replicate the reference's fp16-autocast path:
+//   v = fp16(acc + bias); v = fp16(v + temb[b,n]); s = fp16(acc_sc + bias_sc); v = fp16(s + v); v = fp16(v + res)
+#include "common.cuh"
+#include "host.h"
+
+namespace vton {
+
+struct GemmParams {
+  __half* out;
+  int ld_out;
+  int M, N;  // output rows / accumulator columns (GEGLU: N = 2 * out columns)
+  const __half* bias;
+  const __half* bias_sc;
+  const __half* residual;
+  int ld_res;
+  const __half* rowvec;  // per-sample row vector added after the bias rounding (time embedding), [B, ld_rowvec]
+  int ld_rowvec;
+  int rows_per_sample;
+  int slabs_main;  // 64-wide K slabs accumulated into accumulator 0
+  int slabs_sc;    // slabs accumulated into accumulator 1 (1x1 shortcut), 0 = none
+  int sc_split;    // shortcut slabs taken from source 0 before switching to source 1
+  // conv geometry
+  int conv;
+  int H, W, B;
+  int bw, bh, bb;  // TMA box extent in x / y / batch (bw*bh*bb == 128)
+  int tiles_x, tiles_y;
+  int cin_slabs;  // Cin / 64
+  int cout;       // rows per tap in the packed weight
+  int n_tiles;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN, int STAGES, bool GEGLU>
+__global__ void __launch_bounds__(192, 1)
+gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
+                 const __grid_constant__ CUtensorMap tmBs, const GemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t acc_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int n_tile = tile % p.n_tiles;
+  const int m_tile = tile / p.n_tiles;
+  const int n0 = n_tile * BN;
+  const int total_slabs = p.slabs_main + p.slabs_sc;
+  constexpr uint32_t kTmemCols = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);  // room for the shortcut accumulator
+
+  // conv tile origin
+  int b0 = 0, y0 = 0, x0 = 0;
+  if (p.conv) {
+    const int tx = m_tile % p.tiles_x;
+    const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+    const int tb = m_tile / (p.tiles_x * p.tiles_y);
+    x0 = tx * p.bw;
+    y0 = ty * p.bh;
+    b0 = tb * p.bb;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.slabs_sc) {
+      tma_prefetch_desc(&tmS0);
+      tma_prefetch_desc(&tmS1);
+      tma_prefetch_desc(&tmBs);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int s = 0; s < total_slabs; ++s) {
+        const int stage = s % STAGES;
+        const uint32_t phase = (s / STAGES) & 1;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+        const uint32_t b_dst = a_dst + A_BYTES;
+        mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+        if (s < p.slabs_main) {
+          if (p.conv) {
+            const int tap = s / p.cin_slabs;
+            const int c0 = (s - tap * p.cin_slabs) * BK;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 + dx, y0 + dy, b0);
+            tma_load_2d(b_dst, &tmB, full_bar(stage), c0, tap * p.cout + n0);
+          } else {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), s * BK, m_tile * BM);
+            tma_load_2d(b_dst, &tmB, full_bar(stage), s * BK, n0);
+          }
+        } else {
+          const int ss = s - p.slabs_main;
+          if (ss < p.sc_split)
+            tma_load_4d(a_dst, &tmS0, full_bar(stage), ss * BK, x0, y0, b0);
+          else
+            tma_load_4d(a_dst, &tmS1, full_bar(stage), (ss - p.sc_split) * BK, x0, y0, b0);
+          tma_load_2d(b_dst, &tmBs, full_bar(stage), ss * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0);
+      for (int s = 0; s < total_slabs; ++s) {
+        const int stage = s % STAGES;
+        const uint32_t phase = (s / STAGES) & 1;
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_src = smem_base + stage * L::STAGE_BYTES;
+        const uint32_t b_src = a_src + A_BYTES;
+        const bool sc = s >= p.slabs_main;
+        const uint32_t d = tmem_base + (sc ? BN : 0);
+        const int s_local = sc ? s - p.slabs_main : s;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t a_desc = make_smem_desc_sw128(a_src + k * 32, 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(b_src + k * 32, 0, 1024);
+          tc_mma_f16(d, a_desc, b_desc, idesc, (s_local > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+      }
+      tc_commit(acc_bar);  // accumulators complete
+    }
+  } else {
+    // ===================== epilogue (4 warps, thread = accumulator row) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r_local = quarter * 32 + lane;
+    long long out_row = -1;
+    int sample = 0;
+    if (p.conv) {
+      const int lx = r_local % p.bw;
+      const int ly = (r_local / p.bw) % p.bh;
+      const int lb = r_local / (p.bw * p.bh);
+      const int b = b0 + lb, y = y0 + ly, x = x0 + lx;
+      if (b < p.B && y < p.H && x < p.W) out_row = (static_cast<long long>(b) * p.H + y) * p.W + x;
+      sample = b;
+    } else {
+      const int m = m_tile * BM + r_local;
+      if (m < p.M) out_row = m;
+      sample = p.rows_per_sample > 0 ? m / p.rows_per_sample : 0;
+    }
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+    const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
+    const int out_N = GEGLU ? p.N / 2 : p.N;
+#pragma unroll 1
+    for (int c = 0; c < OUT_COLS / 32; ++c) {
+      uint32_t acc[32];
+      uint32_t acc2[32];
+      tmem_ld_32x32(t_row + c * 32, acc);
+      if (GEGLU) {
+        tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
+      } else if (p.slabs_sc) {
+        tmem_ld_32x32(t_row + BN + c * 32, acc2);
+      }
+      tmem_ld_wait();
+      if (out_row < 0) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
+        if (ncol >= out_N) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+        if (GEGLU) {
+          const int bcol = n0 + c * 32 + g * 8;  // packed (interleaved) bias index of the value half
+          float gt[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(acc2[g * 8 + j]);
+          if (p.bias) {
+            const uint4 bh = *reinterpret_cast<const uint4*>(p.bias + bcol);
+            const uint4 bg = *reinterpret_cast<const uint4*>(p.bias + bcol + BN / 2);
+            const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w};
+            const uint32_t bgw[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(bhw[j]);
+              const float2 b = unpack_h2(bgw[j]);
+              v[2 * j] += a.x;
+              v[2 * j + 1] += a.y;
+              gt[2 * j] += b.x;
+              gt[2 * j + 1] += b.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float hv = round_h(v[j]);
+            const float gv = round_h(gt[j]);
+            v[j] = hv * round_h(gelu_erf_f(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
+          }
+        } else {
+          if (p.bias) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + ncol);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(bw[j]);
+              v[2 * j] += a.x;
+              v[2 * j + 1] += a.y;
+            }
+          }
+          if (p.rowvec) {
+            const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
+            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(tw[j]);
+              v[2 * j] = round_h(v[2 * j]) + a.x;
+              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+            }
+          }
+          if (p.slabs_sc) {
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
+            if (p.bias_sc) {
+              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias_sc + ncol);
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 a = unpack_h2(bw[j]);
+                s[2 * j] += a.x;
+                s[2 * j + 1] += a.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
+          }
+          if (p.residual) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(rw[j]);
+              v[2 * j] = round_h(v[2 * j]) + a.x;
+              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+            }
+          }
+        }
+        uint4 o;
+        o.x = pack_h2(v[0], v[1]);
+        o.y = pack_h2(v[2], v[3]);
+        o.z = pack_h2(v[4], v[5]);
+        o.w = pack_h2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.out + out_row * p.ld_out + ncol) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool GEGLU>
+static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS0,
+                          const CUtensorMap& tmS1, const CUtensorMap& tmBs, const GemmParams& p, int grid,
+                          cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gemm_conv_kernel<BN, STAGES, GEGLU>;
+  static bool configured = false;
+  if (!configured) {
+    VTON_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmS0, tmS1, tmBs, p);
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+static int pick_bn(int N, int force_bn) {
+  if (force_bn) return force_bn;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 160 == 0) return 160;
+  if (N <= 64) return 64;
+  return 128;
+}
+
+static int dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS0,
+                    const CUtensorMap& tmS1, const CUtensorMap& tmBs, GemmParams& p, int m_tiles,
+                    cudaStream_t stream) {
+  p.n_tiles = cdiv(p.N, bn);
+  const int grid = m_tiles * p.n_tiles;
+  if (geglu) {
+    if (bn == 128) return launch_variant<128, 3, true>(tmA, tmB, tmS0, tmS1, tmBs, p, grid, stream);
+    if (bn == 256) return launch_variant<256, 4, true>(tmA, tmB, tmS0, tmS1, tmBs, p, grid, stream);
+    set_last_error("GEGLU epilogue supports BN 128/256 only (got %d)", bn);
+    return kErrUnsupported;
+  }
+  switch (bn) {
+    case 64: return launch_variant<64, 4, false>(tmA, tmB, tmS0, tmS1, tmBs, p, grid, stream);
+    case 128: return launch_variant<128, 3, false>(tmA, tmB, tmS0, tmS1, tmBs, p, grid, stream);
+    case 160: return launch_variant<160, 3, false>(tmA, tmB, tmS0, tmS1, tmBs, p, grid, stream);
+    case 256: return launch_variant<256, 4, false>(tmA, tmB, tmS0, tmS1, tmBs, p, grid, stream);
+  }
+  set_last_error("unsupported BN %d", bn);
+  return kErrUnsupported;
+}
+
+int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
+                  int K, const void* bias, const void* residual, long long ldr, const void* rowvec, long long ld_rowvec,
+                  int rows_per_sample, int geglu, int force_bn, cudaStream_t stream) {
+  VTON_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VTON_CHECK_ARG(K % 64 == 0, "gemm: K=%d must be a multiple of 64", K);
+  VTON_CHECK_ARG(N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "gemm: N/lda/ldw/ldo must be multiples of 8");
+  VTON_CHECK_ARG(!geglu || (N % 16 == 0 && !residual && !rowvec), "gemm: bad GEGLU configuration");
+  int bn = pick_bn(N, force_bn);
+  if (geglu && bn != 128 && bn != 256) bn = 128;
+  VTON_CHECK_ARG(!geglu || N % bn == 0, "gemm: GEGLU needs N %% BN == 0 (N=%d, BN=%d)", N, bn);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {64, 128};
+    if (int e = encode_tmap_f16(&tmA, A, 2, dims, strides, box)) return e;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    if (int e = encode_tmap_f16(&tmB, W, 2, dims, strides, box)) return e;
+  }
+  GemmParams p{};
+  p.out = static_cast<__half*>(out);
+  p.ld_out = static_cast<int>(ldo);
+  p.M = M;
+  p.N = N;
+  p.bias = static_cast<const __half*>(bias);
+  p.residual = static_cast<const __half*>(residual);
+  p.ld_res = static_cast<int>(ldr);
+  p.rowvec = static_cast<const __half*>(rowvec);
+  p.ld_rowvec = static_cast<int>(ld_rowvec);
+  p.rows_per_sample = rows_per_sample;
+  p.slabs_main = K / 64;
+  return dispatch(bn, geglu != 0, tmA, tmB, tmA, tmA, tmB, p, cdiv(M, BM), stream);
+}
+
+static void pick_box(int B, int H, int W, int* bw, int* bh, int* bb) {
+  int w = 1;
+  while (w < 128 && W % (w * 2) == 0) w *= 2;
+  int h = 1;
+  while (w * h < 128 && h * 2 <= H) h *= 2;
+  *bw = w;
+  *bh = h;
+  *bb = 128 / (w * h);
+  (void)B;
+}
+
+static int encode_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W, int C, int ldc, int bw, int bh, int bb) {
+  uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                      static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(ldc) * 2, static_cast<uint64_t>(W) * ldc * 2,
+                         static_cast<uint64_t>(H) * W * ldc * 2};
+  uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+  return encode_tmap_f16(tm, base, 4, dims, strides, box);
+}
+
+// x: [B,H,W,Cin] (channel stride ldx), w: [9][Cout][Cin] fp16 (tap-major), out: [B*H*W, ldo]
+int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                 const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
+                 const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
+                 cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv3x3: empty input");
+  VTON_CHECK_ARG(Cin % 64 == 0, "conv3x3: Cin=%d must be a multiple of 64 (pad channels)", Cin);
+  VTON_CHECK_ARG(Cout % 8 == 0 && ldo % 8 == 0 && ldx % 8 == 0, "conv3x3: Cout/ldo/ldx must be multiples of 8");
+  VTON_CHECK_ARG(C0 % 64 == 0 && C1 % 64 == 0, "conv3x3: shortcut source channels must be multiples of 64");
+  VTON_CHECK_ARG(!(w_sc && residual), "conv3x3: shortcut conv and identity residual are exclusive");
+  const int bn = pick_bn(Cout, force_bn);
+  int bw, bh, bb;
+  pick_box(B, H, W, &bw, &bh, &bb);
+  CUtensorMap tmA, tmB, tmS0, tmS1, tmBs;
+  if (int e = encode_nhwc(&tmA, x, B, H, W, Cin, static_cast<int>(ldx), bw, bh, bb)) return e;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(9) * Cout};
+    uint64_t strides[1] = {static_cast<uint64_t>(Cin) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    if (int e = encode_tmap_f16(&tmB, w, 2, dims, strides, box)) return e;
+  }
+  tmS0 = tmA;
+  tmS1 = tmA;
+  tmBs = tmB;
+  GemmParams p{};
+  if (w_sc) {
+    VTON_CHECK_ARG(sc0 && C0 > 0, "conv3x3: shortcut needs a source");
+    if (int e = encode_nhwc(&tmS0, sc0, B, H, W, C0, C0, bw, bh, bb)) return e;
+    if (sc1 && C1 > 0) {
+      if (int e = encode_nhwc(&tmS1, sc1, B, H, W, C1, C1, bw, bh, bb)) return e;
+    }
+    const int Csc = C0 + (sc1 ? C1 : 0);
+    uint64_t dims[2] = {static_cast<uint64_t>(Csc), static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {static_cast<uint64_t>(Csc) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    if (int e = encode_tmap_f16(&tmBs, w_sc, 2, dims, strides, box)) return e;
+    p.slabs_sc = Csc / 64;
+    p.sc_split = C0 / 64;
+  }
+  p.out = static_cast<__half*>(out);
+  p.ld_out = static_cast<int>(ldo);
+  p.M = B * H * W;
+  p.N = Cout;
+  p.bias = static_cast<const __half*>(bias);
+  p.bias_sc = static_cast<const __half*>(bias_sc);
+  p.residual = static_cast<const __half*>(residual);
+  p.ld_res = static_cast<int>(ldr);
+  p.rowvec = static_cast<const __half*>(temb);
+  p.ld_rowvec = static_cast<int>(ld_temb);
+  p.slabs_main = 9 * (Cin / 64);
+  p.conv = 1;
+  p.H = H;
+  p.W = W;
+  p.B = B;
+  p.bw = bw;
+  p.bh = bh;
+  p.bb = bb;
+  p.tiles_x = W / bw;
+  p.tiles_y = cdiv(H, bh);
+  p.cin_slabs = Cin / 64;
+  p.cout = Cout;
+  const int m_tiles = p.tiles_x * p.tiles_y * cdiv(B, bb);
+  return dispatch(bn, false, tmA, tmB, tmS0, tmS1, tmBs, p, m_tiles, stream);
+}
+
+}  // namespace vton

@@ -1,0 +1,75 @@
+// Host-side plumbing for libb200vton.so: last-error string and TMA descriptor encoding.
+// cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint), so the library has no link-time
+// dependency on libcuda and loads on a machine without a driver (the CPU build/"symbols export" check).
+#include "host.h"
+
+#include <mutex>
+
+namespace vton {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return kErrCuda;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_last_error("tensor map base %p is not 16-byte aligned", base);
+    return kErrInvalid;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t gbox[5];
+  cuuint32_t gel[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    gbox[i] = box[i];
+    gel[i] = elem_strides ? elem_strides[i] : 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_last_error("tensor map stride %llu not a multiple of 16 bytes", (unsigned long long)gstr[i - 1]);
+        return kErrInvalid;
+      }
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, gbox, gel, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return kErrCuda;
+  }
+  return kOk;
+}
+
+}  // namespace vton

@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA descriptor encode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace vton {
+
+// error codes returned through the C ABI (0 = success)
+enum : int { kOk = 0, kErrInvalid = 1, kErrCuda = 2, kErrUnsupported = 3 };
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+#define VTON_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      vton::set_last_error(__VA_ARGS__); \
+      return vton::kErrInvalid;        \
+    }                                  \
+  } while (0)
+
+#define VTON_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      vton::set_last_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return vton::kErrCuda;                                                                     \
+    }                                                                                            \
+  } while (0)
+
+// Encodes a tiled fp16 tensor map with SWIZZLE_128B (inner box must be 64 halves = 128 B).
+// dims/strides innermost-first; strides in BYTES for dims 1..rank-1. Returns 0 on success.
+int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides = nullptr);
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace vton

@@ -1,0 +1,246 @@
+// GroupNorm(32) (+SiLU) and LayerNorm for the UNets' NHWC / token-major fp16 activations (sm_100a, HBM-bound).
+//
+// Reference rounding points: under torch.cuda.amp.autocast the norms run in fp32 on the fp16
+// input and return fp32; SiLU stays fp32; the consuming conv / linear casts to fp16. So both kernels compute in fp32
+// and round ONCE to fp16 on store.
+//   GroupNorm: diffusers ResnetBlock2D norm1/norm2 (+SiLU), Transformer2DModel.norm (eps 1e-6, no act;
+//              src/transformerhacked_tryon.py:148,329), conv_norm_out (src/unet_hacked_tryon.py:744,1384-1385).
+//              The input may be the channel-concat of two tensors (up-block skip, src/unet_block_hacked_tryon.py:2346)
+//              which is never materialised: both sources are read in place.
+//   LayerNorm: BasicTransformerBlock.norm1/2/3 (src/attentionhacked_tryon.py:310,365,390), eps 1e-5.
+#include "common.cuh"
+#include "host.h"
+
+namespace vton {
+
+constexpr int GN_THREADS = 512;
+constexpr int GN_GROUPS = 32;
+
+struct GnSrc {
+  const __half* x0;
+  const __half* x1;
+  int C0, C1;  // channels of each source (C1 = 0: single source)
+};
+
+__device__ __forceinline__ uint4 gn_load(const GnSrc& s, long long row, int v) {
+  const int c = v * 8;
+  if (c < s.C0) return *reinterpret_cast<const uint4*>(s.x0 + row * s.C0 + c);
+  return *reinterpret_cast<const uint4*>(s.x1 + row * s.C1 + (c - s.C0));
+}
+
+// stats[b][g][0] = sum, [1] = sum of squares (double, pre-zeroed)
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int rows_per_cta, double* stats) {
+  const int C = src.C0 + src.C1;
+  const int V = C / 8;
+  const int cpg = C / GN_GROUPS;
+  const int row_lanes = GN_THREADS / V;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(HW, r_begin + rows_per_cta);
+  __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int v = threadIdx.x % V;
+  const int rl = threadIdx.x / V;
+  if (rl < row_lanes) {
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    for (int r = r_begin + rl; r < r_end; r += row_lanes) {
+      const uint4 u = gn_load(src, static_cast<long long>(b) * HW + r, v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_h2(w[j]);
+        sum[2 * j] += f.x;
+        sq[2 * j] += f.x * f.x;
+        sum[2 * j + 1] += f.y;
+        sq[2 * j + 1] += f.y * f.y;
+      }
+    }
+    // fold the 8 channels into their groups (a vector may straddle two groups)
+    int g_prev = (v * 8) / cpg;
+    float acc_s = 0.f, acc_q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&s_sum[g_prev], acc_s);
+        atomicAdd(&s_sq[g_prev], acc_q);
+        acc_s = acc_q = 0.f;
+        g_prev = g;
+      }
+      acc_s += sum[j];
+      acc_q += sq[j];
+    }
+    atomicAdd(&s_sum[g_prev], acc_s);
+    atomicAdd(&s_sq[g_prev], acc_q);
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    atomicAdd(&stats[(static_cast<long long>(b) * GN_GROUPS + threadIdx.x) * 2 + 0], static_cast<double>(s_sum[threadIdx.x]));
+    atomicAdd(&stats[(static_cast<long long>(b) * GN_GROUPS + threadIdx.x) * 2 + 1], static_cast<double>(s_sq[threadIdx.x]));
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* stats, const __half* gamma, const __half* beta,
+                float eps, int silu, __half* out) {
+  const int C = src.C0 + src.C1;
+  const int V = C / 8;
+  const int cpg = C / GN_GROUPS;
+  const int row_lanes = GN_THREADS / V;
+  const int b = blockIdx.y;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(HW, r_begin + rows_per_cta);
+  const int v = threadIdx.x % V;
+  const int rl = threadIdx.x / V;
+  if (rl >= row_lanes) return;
+  float sc[8], sh[8];
+  const double n = static_cast<double>(cpg) * HW;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j;
+    const int g = c / cpg;
+    const double s = stats[(static_cast<long long>(b) * GN_GROUPS + g) * 2 + 0];
+    const double q = stats[(static_cast<long long>(b) * GN_GROUPS + g) * 2 + 1];
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = rsqrtf(static_cast<float>(var) + eps);
+    const float gm = gamma ? h2f(gamma[c]) : 1.f;
+    const float bt = beta ? h2f(beta[c]) : 0.f;
+    sc[j] = rstd * gm;
+    sh[j] = bt - static_cast<float>(mean) * sc[j];
+  }
+  for (int r = r_begin + rl; r < r_end; r += row_lanes) {
+    const long long row = static_cast<long long>(b) * HW + r;
+    const uint4 u = gn_load(src, row, v);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_h2(w[j]);
+      y[2 * j] = f.x * sc[2 * j] + sh[2 * j];
+      y[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+    }
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+    }
+    uint4 o;
+    o.x = pack_h2(y[0], y[1]);
+    o.y = pack_h2(y[2], y[3]);
+    o.z = pack_h2(y[4], y[5]);
+    o.w = pack_h2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(out + row * C + v * 8) = o;
+  }
+}
+
+int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma, const void* beta,
+                   float eps, int silu, void* stats_ws, void* out, cudaStream_t stream) {
+  const int C = C0 + C1;
+  VTON_CHECK_ARG(B > 0 && HW > 0 && C > 0, "groupnorm: empty input");
+  VTON_CHECK_ARG(C % GN_GROUPS == 0 && C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: C=%d must divide into 32 groups, sources multiple of 8", C);
+  VTON_CHECK_ARG(C / 8 <= GN_THREADS, "groupnorm: C=%d too wide", C);
+  VTON_CHECK_ARG(stats_ws != nullptr, "groupnorm: stats workspace (B*32*2 doubles) required");
+  GnSrc src{static_cast<const __half*>(x0), static_cast<const __half*>(x1), C0, C1};
+  int chunks = 296 / B;
+  if (chunks < 1) chunks = 1;
+  if (chunks > cdiv(HW, 16)) chunks = cdiv(HW, 16);
+  const int rows_per_cta = cdiv(HW, chunks);
+  chunks = cdiv(HW, rows_per_cta);
+  VTON_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * GN_GROUPS * B, stream));
+  dim3 grid(chunks, B);
+  gn_stats_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<double*>(stats_ws));
+  gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<const double*>(stats_ws),
+                                                   static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                                                   eps, silu, static_cast<__half*>(out));
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, values held in registers (C <= 2048)
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAX_VEC = 8;  // per lane: up to 8 x 8 halves => C <= 2048
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* x, long long ldx, int rows, int C, const __half* gamma, const __half* beta, float eps,
+                 __half* out, long long ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int V = C / 8;
+  float val[LN_MAX_VEC][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_h2(w[j]);
+        val[i][2 * j] = f.x;
+        val[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = val[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      const uint4 g = gamma ? *reinterpret_cast<const uint4*>(gamma + v * 8) : make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+      const uint4 bt = beta ? *reinterpret_cast<const uint4*>(beta + v * 8) : make_uint4(0, 0, 0, 0);
+      const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+      const uint32_t bw[4] = {bt.x, bt.y, bt.z, bt.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 gg = unpack_h2(gw[j]);
+        const float2 bb = unpack_h2(bw[j]);
+        const float y0 = (val[i][2 * j] - mean) * rstd * gg.x + bb.x;
+        const float y1 = (val[i][2 * j + 1] - mean) * rstd * gg.y + bb.y;
+        ow[j] = pack_h2(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(out + row * ldo + v * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+}
+
+int layernorm_impl(const void* x, long long ldx, int rows, int C, const void* gamma, const void* beta, float eps,
+                   void* out, long long ldo, cudaStream_t stream) {
+  VTON_CHECK_ARG(rows > 0 && C > 0, "layernorm: empty input");
+  VTON_CHECK_ARG(C % 8 == 0 && C <= LN_MAX_VEC * 256 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: C=%d unsupported", C);
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(static_cast<const __half*>(x), ldx, rows, C,
+                                                     static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                                                     eps, static_cast<__half*>(out), ldo);
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace vton

@@ -1,0 +1,272 @@
+"""ctypes binding of libb200vton.so (include/b200vton.h) plus thin torch-tensor wrappers.
+
+PyTorch is used for device memory and streams only: every wrapper passes `tensor.data_ptr()` and the current CUDA
+stream to the C ABI. There is no fallback: if the library is missing or an op fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200vton.so")
+
+_c = ctypes
+_vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+# name -> argtypes; restype is int for every op. Mirrors include/b200vton.h one to one.
+SIGNATURES = {
+    "b200vton_gemm_f16": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
+    "b200vton_conv3x3_nhwc": [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64,
+                              _vp, _i64, _i, _vp],
+    "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
+    "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
+    "b200vton_nchw_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
+    "b200vton_nhwc_to_nchw": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "b200vton_upsample2x_nhwc": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "b200vton_im2col3x3_s2_nhwc": [_vp, _i, _i, _i, _i, _vp, _vp],
+    "b200vton_timestep_embedding": [_vp, _i, _i, _i, _vp, _vp],
+    "b200vton_skinny_linear": [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp],
+    "b200vton_cfg_ddpm_step": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
+}
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) libb200vton.so and declare every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension must be built (python idm-vton_b200/build.py); "
+                           "there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.b200vton_version.restype = _i
+    lib.b200vton_last_error.restype = _c.c_char_p
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _i
+    _lib = lib
+    return lib
+
+
+def _check(rc, name):
+    if rc != 0:
+        msg = _lib.b200vton_last_error().decode()
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f16(t, name):
+    if t is not None:
+        if t.dtype != torch.float16 or not t.is_cuda:
+            raise TypeError(f"{name} must be a CUDA fp16 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# op wrappers
+# ------------------------------------------------------------------------------------------------
+def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=False, out=None, force_bn=0):
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T). a / residual / out may be row-strided 2-D views (last dim contiguous)."""
+    lib = load()
+    _f16(a, "a"); _f16(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    if residual is not None:
+        assert residual.shape == (M, n_out) and residual.stride(1) == 1
+    rc = lib.b200vton_gemm_f16(_p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+                               _p(residual), residual.stride(0) if residual is not None else 0, _p(rowvec),
+                               rowvec.stride(0) if rowvec is not None else 0, rows_per_sample, int(geglu), force_bn,
+                               _stream())
+    _check(rc, "b200vton_gemm_f16")
+    return out
+
+
+def conv3x3(x, w_packed, bias=None, temb=None, sc0=None, sc1=None, w_sc=None, bias_sc=None, residual=None, out=None,
+            force_bn=0):
+    """x: [B,H,W,Cin] NHWC fp16 (contiguous); w_packed: [9,Cout,Cin]; returns [B,H,W,Cout]."""
+    lib = load()
+    _f16(x, "x"); _f16(w_packed, "w_packed")
+    B, H, W, Cin = x.shape
+    assert x.is_contiguous() and w_packed.is_contiguous() and w_packed.shape[0] == 9 and w_packed.shape[2] == Cin
+    Cout = w_packed.shape[1]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x.device)
+    C0 = sc0.shape[-1] if sc0 is not None else 0
+    C1 = sc1.shape[-1] if sc1 is not None else 0
+    rc = lib.b200vton_conv3x3_nhwc(_p(x), Cin, B, H, W, Cin, _p(w_packed), Cout, _p(bias), _p(temb),
+                                   temb.stride(0) if temb is not None else 0, _p(sc0), C0, _p(sc1), C1, _p(w_sc),
+                                   _p(bias_sc), _p(residual), residual.shape[-1] if residual is not None else 0,
+                                   _p(out), out.shape[-1], force_bn, _stream())
+    _check(rc, "b200vton_conv3x3_nhwc")
+    return out
+
+
+def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=None, accumulate=False, out=None):
+    """q: [B,Nq,*], k0/v0: [B,N0,*], k1/v1: [B1,N1,*] 3-D views with contiguous last dim (row strides may exceed
+    heads*64, e.g. slices of a fused QKV buffer). n1 > 0 with k1 None => all-zero segment-1 tokens for every sample."""
+    lib = load()
+    B, Nq = q.shape[0], q.shape[1]
+    N0 = k0.shape[1]
+    H = heads
+    assert q.stride(2) == 1 and k0.stride(2) == 1 and v0.stride(2) == 1
+    assert q.stride(0) == Nq * q.stride(1) and k0.stride(0) == N0 * k0.stride(1) and v0.stride() == k0.stride()
+    if scale is None:
+        scale = 64 ** -0.5
+    if out is None:
+        out = torch.empty((B, Nq, H * 64), dtype=torch.float16, device=q.device)
+    B1 = 0
+    ld1 = 0
+    if k1 is not None:
+        B1, n1 = k1.shape[0], k1.shape[1]
+        ld1 = k1.stride(1)
+        assert k1.stride(2) == 1 and k1.stride(0) == n1 * ld1 and v1.stride() == k1.stride()
+    rc = lib.b200vton_attention(_p(q), q.stride(1), _p(k0), _p(v0), k0.stride(1), _p(k1), _p(v1), ld1, _p(out),
+                                out.stride(1), B, H, Nq, N0, n1, B1, kv1_off, float(scale), int(accumulate), _stream())
+    _check(rc, "b200vton_attention")
+    return out
+
+
+_gn_ws = {}
+
+
+def _stats_ws(device, B):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < B * 64:
+        ws = torch.empty(max(B, 16) * 64, dtype=torch.float64, device=device)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x0, gamma, beta, eps, silu, x1=None, out=None, ws=None):
+    """x0: [B,HW,C0] (or [B,H,W,C0]) contiguous, optional x1 [B,HW,C1]: GroupNorm(32) over the channel concat."""
+    lib = load()
+    B = x0.shape[0]
+    C0 = x0.shape[-1]
+    HW = x0.numel() // (B * C0)
+    C1 = x1.shape[-1] if x1 is not None else 0
+    assert x0.is_contiguous() and (x1 is None or x1.is_contiguous())
+    if out is None:
+        out = torch.empty(x0.shape[:-1] + (C0 + C1,), dtype=torch.float16, device=x0.device)
+    if ws is None:
+        ws = _stats_ws(x0.device, B)
+    rc = lib.b200vton_groupnorm(_p(x0), C0, _p(x1), C1, B, HW, _p(gamma), _p(beta), float(eps), int(silu), _p(ws),
+                                _p(out), _stream())
+    _check(rc, "b200vton_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    lib = load()
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    assert x2.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    o2 = out.reshape(-1, C)
+    rc = lib.b200vton_layernorm(_p(x2), x2.stride(0), x2.shape[0], C, _p(gamma), _p(beta), float(eps), _p(o2),
+                                o2.stride(0), _stream())
+    _check(rc, "b200vton_layernorm")
+    return out
+
+
+def nchw_to_nhwc(src, dst, c_off=0):
+    """dst[s,y,x,c_off+c] = src[s % Bs, c, y, x]; dst: [Bd,H,W,ldc] contiguous."""
+    lib = load()
+    Bs, Cs, H, W = src.shape
+    assert src.is_contiguous() and dst.is_contiguous()
+    rc = lib.b200vton_nchw_to_nhwc(_p(src), Bs, Cs, H, W, _p(dst), dst.shape[0], dst.shape[-1], c_off, _stream())
+    _check(rc, "b200vton_nchw_to_nhwc")
+    return dst
+
+
+def nhwc_to_nchw(src, C, out=None):
+    lib = load()
+    B, H, W, ldc = src.shape
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=torch.float16, device=src.device)
+    rc = lib.b200vton_nhwc_to_nchw(_p(src), B, C, H, W, ldc, _p(out), _stream())
+    _check(rc, "b200vton_nhwc_to_nchw")
+    return out
+
+
+def upsample2x(x, out=None):
+    lib = load()
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float16, device=x.device)
+    rc = lib.b200vton_upsample2x_nhwc(_p(x), B, H, W, C, _p(out), _stream())
+    _check(rc, "b200vton_upsample2x_nhwc")
+    return out
+
+
+def im2col3x3_s2(x, out=None):
+    lib = load()
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((B * Ho * Wo, 9 * C), dtype=torch.float16, device=x.device)
+    rc = lib.b200vton_im2col3x3_s2_nhwc(_p(x), B, H, W, C, _p(out), _stream())
+    _check(rc, "b200vton_im2col3x3_s2_nhwc")
+    return out
+
+
+def timestep_embedding(values, dim, rows_repeat=1, out=None):
+    """values: fp32 CUDA tensor [n]; returns [n*rows_repeat, dim] fp16 ([cos|sin])."""
+    lib = load()
+    assert values.dtype == torch.float32 and values.is_cuda
+    n = values.numel()
+    if out is None:
+        out = torch.empty((n * rows_repeat, dim), dtype=torch.float16, device=values.device)
+    rc = lib.b200vton_timestep_embedding(_p(values), n, dim, rows_repeat, _p(out), _stream())
+    _check(rc, "b200vton_timestep_embedding")
+    return out
+
+
+def skinny_linear(x, w, bias=None, in_silu=False, out_silu=False, addend=None, out=None):
+    lib = load()
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    rc = lib.b200vton_skinny_linear(_p(x), x.stride(0), M, K, _p(w), w.stride(0), N, _p(bias), int(in_silu),
+                                    int(out_silu), _p(addend), addend.stride(0) if addend is not None else 0, _p(out),
+                                    out.stride(0), _stream())
+    _check(rc, "b200vton_skinny_linear")
+    return out
+
+
+def cfg_ddpm_step(eps, latents, noise, coef, do_cfg=True, out=None):
+    """eps: [2B,H,W,ldc] NHWC (or [B,...] without CFG); latents/noise: [B,C,H,W]; coef: 6 fp32 on device."""
+    lib = load()
+    B, C, H, W = latents.shape
+    if out is None:
+        out = torch.empty_like(latents)
+    rc = lib.b200vton_cfg_ddpm_step(_p(eps), eps.shape[-1], B, C, H, W, _p(latents), _p(noise), _p(coef), int(do_cfg),
+                                    _p(out), _stream())
+    _check(rc, "b200vton_cfg_ddpm_step")
+    return out

@@ -1,0 +1,107 @@
+/* libb200vton.so — C ABI of the Blackwell-native IDM-VTON denoising engine.
+ *
+ * The reference (yisol/IDM-VTON) has no C/FFI plugin API; its seams are Python protocols (pipeline
+ * __call__, UNet2DConditionModel.forward, the diffusers attention-processor protocol). This header is the boundary the
+ * Python host (idm-vton_b200/*.py, loaded with ctypes) binds instead of the ATen/cuDNN/cuBLAS/SDPA library calls the
+ * reference issues. Every entry point cites the reference call site it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to fp16 data unless stated; the caller (PyTorch) owns every buffer;
+ *     the library never allocates or frees device memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); launches are asynchronous and may be
+ *     captured into a CUDA graph;
+ *   - return value 0 = success, non-zero = error (1 invalid argument, 2 CUDA error, 3 unsupported shape);
+ *     b200vton_last_error() returns the message for the calling thread. There is no CPU fallback.
+ *   - activations are NHWC / token-major: a feature map [B,H,W,C] and a token matrix [B*H*W, C] are the same memory.
+ */
+#ifndef B200VTON_H_
+#define B200VTON_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int b200vton_version(void);
+const char* b200vton_last_error(void);
+
+/* out[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear on the hot path — attn to_q/to_k/to_v/to_out
+ * (ip_adapter/attention_processor.py:240-268), Transformer2DModel.proj_in/proj_out
+ * (src/transformerhacked_tryon.py:331-345,410-427), FeedForward GEGLU / net.2 (src/attentionhacked_tryon.py:621-679).
+ * epi: v = fp16(acc + bias[n]); v = fp16(v + rowvec[m / rows_per_sample, n]); v = fp16(v + residual[m, n]).
+ * geglu != 0: W/bias rows are tile-interleaved [value | gate] (see engine.pack_geglu) and
+ *             out[M, N/2] = fp16(value) * fp16(gelu_erf(fp16(gate))).
+ * K % 64 == 0; N, lda, ldw, ldo % 8 == 0. force_bn: 0 = auto tile width, else 64/128/160/256. */
+int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N,
+                      int K, const void* bias, const void* residual, int64_t ldr, const void* rowvec,
+                      int64_t ld_rowvec, int rows_per_sample, int geglu, int force_bn, void* stream);
+
+/* NHWC 3x3 convolution, stride 1, pad 1, as implicit GEMM: diffusers ResnetBlock2D.conv1/conv2 (+conv_shortcut),
+ * conv_in / conv_out (src/unet_hacked_tryon.py:416,755,1245,1386), the conv of Upsample2D.
+ * x: [B,H,W,Cin] with channel stride ldx; w: [9][Cout][Cin] (tap = ky*3+kx); out: [B*H*W, ldo].
+ * epi: v = fp16(acc + bias); v = fp16(v + temb[b, n]) (time_emb_proj broadcast add);
+ *      1x1 shortcut (w_sc [Cout, C0+C1] over the channel concat of sc0|sc1, accumulated in a second TMEM tile):
+ *      s = fp16(acc_sc + bias_sc); v = fp16(s + v);   identity residual: v = fp16(v + residual[m, n]). */
+int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int Cin, const void* w, int Cout,
+                          const void* bias, const void* temb, int64_t ld_temb, const void* sc0, int C0,
+                          const void* sc1, int C1, const void* w_sc, const void* bias_sc, const void* residual,
+                          int64_t ldr, void* out, int64_t ldo, int force_bn, void* stream);
+
+/* softmax(Q K^T * scale) V, head_dim 64, keys/values streamed from two segments without concatenation:
+ * segment 0 = (k0, v0)[b]; segment 1 = (k1, v1)[(b - kv1_off) % B1] for b >= kv1_off, and for b < kv1_off the N1
+ * tokens are all-zero K/V handled in closed form (CFG-uncond half, src/tryon_pipeline.py:1796).
+ * Replaces cat + F.scaled_dot_product_attention of src/attentionhacked_tryon.py:334-348 /
+ * ip_adapter/attention_processor.py:238-262 (attn1) and :1970-1995 (attn2: call once for the 77 text tokens, once for
+ * the 16 IP tokens with accumulate = 1: out = fp16(out + fp16(result))). Also PerceiverAttention
+ * (ip_adapter/resampler.py:49-78; segment 0 = image tokens, segment 1 = latents).
+ * q: [B,Nq,*] row stride ldq, head h at columns [64h, 64h+64); same for k/v/out. */
+int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v0, int64_t ldkv0, const void* k1,
+                       const void* v1, int64_t ldkv1, void* out, int64_t ldo, int B, int H, int Nq, int N0, int N1,
+                       int B1, int kv1_off, float scale, int accumulate, void* stream);
+
+/* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
+ * fp32 statistics, optional SiLU, fp16 out [B*HW, C0+C1]. stats_ws: B*64 doubles of scratch.
+ * diffusers ResnetBlock2D.norm1/norm2 (+nonlinearity), Transformer2DModel.norm
+ * (src/transformerhacked_tryon.py:329), conv_norm_out + conv_act (src/unet_hacked_tryon.py:1384-1385). */
+int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,
+                       const void* beta, float eps, int silu, void* stats_ws, void* out, void* stream);
+
+/* LayerNorm over the last dim of [rows, C]: BasicTransformerBlock.norm1/2/3
+ * (src/attentionhacked_tryon.py:310,365,390); the garment UNet's norm1 output is the exported garment feature
+ * (src/attentionhacked_garmnet.py:321-322). */
+int b200vton_layernorm(const void* x, int64_t ldx, int rows, int C, const void* gamma, const void* beta, float eps,
+                       void* out, int64_t ldo, void* stream);
+
+/* dst[s,y,x,c_off+c] = src[s % Bs, c, y, x]: NCHW module inputs -> NHWC engine buffer; implements the CFG
+ * duplication and the 13-channel concat of src/tryon_pipeline.py:1769,1777 as batch/channel offsets. */
+int b200vton_nchw_to_nhwc(const void* src, int Bs, int Cs, int H, int W, void* dst, int Bd, int ldc, int c_off,
+                          void* stream);
+/* dst NCHW [B,C,H,W] = src NHWC [B,H,W,ldc][..., :C] */
+int b200vton_nhwc_to_nchw(const void* src, int B, int C, int H, int W, int ldc, void* dst, void* stream);
+
+/* nearest-neighbour x2 (diffusers Upsample2D's F.interpolate), NHWC */
+int b200vton_upsample2x_nhwc(const void* src, int B, int H, int W, int C, void* dst, void* stream);
+/* patches of a 3x3 stride-2 pad-1 conv (diffusers Downsample2D) as A[B*Ho*Wo, 9*C], K ordered tap-major */
+int b200vton_im2col3x3_s2_nhwc(const void* src, int B, int H, int W, int C, void* dst, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[r, :] = [cos | sin](values[r % n] * freq),
+ * values: n fp32 on device; out: [n * rows_repeat, dim] fp16 (src/unet_hacked_tryon.py:1134-1139,1185). */
+int b200vton_timestep_embedding(const void* values, int n, int dim, int rows_repeat, void* out, void* stream);
+
+/* y = W x + b for M <= 16 rows (TimestepEmbedding, add_embedding, batched ResnetBlock2D.time_emb_proj):
+ * x' = in_silu ? fp16(silu(x)) : x; y = fp16(W x' + b); y = out_silu ? fp16(silu(y)) : y; y = fp16(y + addend). */
+int b200vton_skinny_linear(const void* x, int ldx, int M, int K, const void* W, int64_t ldw, int N, const void* bias,
+                           int in_silu, int out_silu, const void* addend, int ld_add, void* out, int ldo,
+                           void* stream);
+
+/* CFG combine + DDPMScheduler.step (src/tryon_pipeline.py:1814-1823). eps NHWC [2B,HW,ldc] (uncond first) or [B,..]
+ * when do_cfg == 0; latents/noise/out NCHW [B,C,H,W] (noise may be NULL); coef: 6 fp32 on device
+ * {guidance_scale, sqrt(1-abar_t), 1/sqrt(abar_t), x0 coeff, x_t coeff, sigma_t}. */
+int b200vton_cfg_ddpm_step(const void* eps, int ldc, int B, int C, int H, int W, const void* latents,
+                           const void* noise, const void* coef, int do_cfg, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VTON_H_ */

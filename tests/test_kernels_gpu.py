@@ -1,0 +1,291 @@
+"""Per-kernel parity of the C-ABI ops (libb200vton.so) against plain PyTorch restatements of the same op with the
+reference's fp16 rounding points. Tolerances: outputs are fp16; a result may differ from the restatement by fp32
+accumulation order only, so we gate at 2 fp16 ulp of the output scale (rtol 2e-3 / atol scaled)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from idm_vton_b200 import lib as L
+    L.load()
+    return L
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
+
+
+def close(a, b, tol=2e-3):
+    a, b = a.float(), b.float()
+    denom = max(1.0, b.abs().max().item())
+    err = (a - b).abs().max().item() / denom
+    assert math.isfinite(err) and err <= tol, f"max scaled err {err:.3e} > {tol}"
+    return err
+
+
+def r16(x):
+    return x.half().float()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 0), (256, 256, 128, 0), (3072, 1280, 1280, 0), (300, 320, 192, 0),
+                                      (1000, 640, 640, 128), (512, 1920, 640, 128), (128, 64, 64, 64),
+                                      (640, 2560, 1280, 256), (77 * 4, 1280, 2048, 0)])
+def test_gemm_plain(lib, M, N, K, bn):
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    out = lib.gemm(a, w, force_bn=bn)
+    ref = a.float() @ w.float().t()
+    close(out, ref)
+
+
+def test_gemm_bias_residual_rowvec(lib):
+    M, N, K = 2 * 768, 1280, 1280
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias, res, rv = rnd(N, seed=3), rnd(M, N, seed=4), rnd(2, N, seed=5)
+    out = lib.gemm(a, w, bias=bias, residual=res, rowvec=rv, rows_per_sample=768)
+    acc = a.float() @ w.float().t()
+    v = r16(acc + bias.float())
+    v = r16(v + rv.float().repeat_interleave(768, 0))
+    v = r16(v + res.float())
+    close(out, v)
+
+
+def test_gemm_strided_views(lib):
+    M, K = 512, 640
+    buf = rnd(M, 3 * K, seed=1)
+    a = buf[:, K:2 * K]
+    w = rnd(640, K, scale=K ** -0.5, seed=2)
+    big = torch.zeros(M, 2 * 640, dtype=torch.float16, device="cuda")
+    out = lib.gemm(a, w, out=big[:, 640:])
+    close(out, a.float() @ w.float().t())
+    assert big[:, :640].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_geglu(lib, bn):
+    from idm_vton_b200.engine import pack_geglu
+    M, C = 640, 640
+    a = rnd(M, C, seed=1)
+    w = rnd(8 * C, C, scale=C ** -0.5, seed=2)
+    b = rnd(8 * C, seed=3)
+    wp, bp = pack_geglu(w, b, bn)
+    out = lib.gemm(a, wp, bias=bp, geglu=True, force_bn=bn)
+    proj = r16(a.float() @ w.float().t() + b.float())
+    h, g = proj.chunk(2, dim=-1)
+    ref = r16(h * r16(F.gelu(g)))
+    close(out, ref)
+
+
+def _conv_ref(x, w, bias):
+    # x NHWC fp16, w [Cout,Cin,3,3] fp16 -> fp32 NHWC
+    y = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), None, padding=1)
+    if bias is not None:
+        y = y + bias.float()[None, :, None, None]
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 24, 64, 320), (1, 16, 16, 128, 64), (4, 8, 8, 320, 640),
+                                            (2, 64, 48, 320, 320), (1, 128, 96, 64, 320), (3, 5, 6, 64, 128),
+                                            (2, 32, 24, 1280, 1280)])
+def test_conv3x3_plain(lib, B, H, W, Cin, Cout):
+    from idm_vton_b200.engine import pack_conv3x3
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = rnd(Cout, seed=3)
+    out = lib.conv3x3(x, pack_conv3x3(w), bias=bias)
+    close(out, _conv_ref(x, w, bias))
+
+
+def test_conv3x3_temb_residual(lib):
+    from idm_vton_b200.engine import pack_conv3x3
+    B, H, W, C = 2, 32, 24, 640
+    x = rnd(B, H, W, C, seed=1)
+    w = rnd(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    bias, temb, res = rnd(C, seed=3), rnd(B, C, seed=4), rnd(B, H, W, C, seed=5)
+    o1 = lib.conv3x3(x, pack_conv3x3(w), bias=bias, temb=temb)
+    ref1 = r16(r16(_conv_ref(x, w, bias)) + temb.float()[:, None, None, :])
+    close(o1, ref1)
+    o2 = lib.conv3x3(x, pack_conv3x3(w), bias=bias, residual=res)
+    ref2 = r16(r16(_conv_ref(x, w, bias)) + res.float())
+    close(o2, ref2)
+
+
+def test_conv3x3_shortcut_two_sources(lib):
+    from idm_vton_b200.engine import pack_conv3x3
+    B, H, W = 2, 16, 24
+    C0, C1, Cout = 640, 320, 640
+    h = rnd(B, H, W, Cout, seed=1)          # normalised conv2 input
+    s0, s1 = rnd(B, H, W, C0, seed=2), rnd(B, H, W, C1, seed=3)
+    w = rnd(Cout, Cout, 3, 3, scale=(9 * Cout) ** -0.5, seed=4)
+    wsc = rnd(Cout, C0 + C1, scale=(C0 + C1) ** -0.5, seed=5)
+    b2, bsc = rnd(Cout, seed=6), rnd(Cout, seed=7)
+    out = lib.conv3x3(h, pack_conv3x3(w), bias=b2, sc0=s0, sc1=s1, w_sc=wsc, bias_sc=bsc)
+    main = r16(_conv_ref(h, w, b2))
+    cat = torch.cat([s0, s1], -1).float()
+    sc = r16(cat @ wsc.float().t() + bsc.float())
+    close(out, r16(sc + main))
+
+
+def _attn_ref(q, k, v, heads, scale, n_zero=0):
+    B, Nq, C = q.shape
+    qh = q.float().view(B, Nq, heads, 64).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, 64).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, 64).transpose(1, 2)
+    if n_zero:
+        kh = torch.cat([kh, torch.zeros(B, heads, n_zero, 64, device=q.device)], 2)
+        vh = torch.cat([vh, torch.zeros(B, heads, n_zero, 64, device=q.device)], 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1)
+    return (p @ vh).transpose(1, 2).reshape(B, Nq, C)
+
+
+@pytest.mark.parametrize("B,H,Nq,N0", [(1, 1, 128, 128), (2, 5, 256, 384), (2, 10, 768, 768), (1, 2, 64, 64),
+                                       (2, 3, 200, 77), (1, 20, 16, 273)])
+def test_attention_single_segment(lib, B, H, Nq, N0):
+    C = H * 64
+    q, k, v = rnd(B, Nq, C, seed=1), rnd(B, N0, C, seed=2), rnd(B, N0, C, seed=3)
+    out = lib.attention(q, k, v, heads=H)
+    close(out, _attn_ref(q, k, v, H, 0.125), tol=3e-3)
+
+
+def test_attention_peaky(lib):
+    B, H, N = 1, 4, 384
+    C = H * 64
+    q, k, v = rnd(B, N, C, scale=4.0, seed=1), rnd(B, N, C, scale=2.0, seed=2), rnd(B, N, C, seed=3)
+    out = lib.attention(q, k, v, heads=H)
+    close(out, _attn_ref(q, k, v, H, 0.125), tol=4e-3)
+
+
+def test_attention_two_segments_and_zero_kv(lib):
+    # try-on attn1: samples [uncond(2) ; cond(2)], garment K/V for 2 garments; uncond half sees zero K/V
+    Bp, H, N, Ng = 2, 5, 256, 384
+    C = H * 64
+    qkv = rnd(2 * Bp, N, 3 * C, seed=1)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    gkv = rnd(Bp, Ng, 2 * C, seed=2)
+    gk, gv = gkv[..., :C], gkv[..., C:]
+    out = lib.attention(q, k, v, gk, gv, kv1_off=Bp, heads=H)
+    ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
+    ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gk], 1), torch.cat([v[Bp:], gv], 1), H, 0.125)
+    close(out[:Bp], ref_u, tol=3e-3)
+    close(out[Bp:], ref_c, tol=3e-3)
+    # dropping the zero tokens instead of the closed form would be visibly wrong:
+    wrong = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125)
+    assert (wrong - ref_u).abs().max() > 10 * (out[:Bp].float() - ref_u).abs().max()
+
+
+def test_attention_shared_garment_modulo(lib):
+    Bp, H, N, Ng = 3, 2, 128, 128
+    C = H * 64
+    q, k, v = rnd(2 * Bp, N, C, seed=1), rnd(2 * Bp, N, C, seed=2), rnd(2 * Bp, N, C, seed=3)
+    gk, gv = rnd(1, Ng, C, seed=4), rnd(1, Ng, C, seed=5)
+    out = lib.attention(q, k, v, gk, gv, kv1_off=Bp, heads=H)
+    ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gk.expand(Bp, -1, -1)], 1),
+                      torch.cat([v[Bp:], gv.expand(Bp, -1, -1)], 1), H, 0.125)
+    close(out[Bp:], ref_c, tol=3e-3)
+
+
+def test_attention_accumulate_decoupled(lib):
+    # attn2: text softmax + IP softmax, fp16 outputs summed in fp16
+    B, H, N = 2, 10, 256
+    C = H * 64
+    q = rnd(B, N, C, seed=1)
+    kt, vt = rnd(B, 77, C, seed=2), rnd(B, 77, C, seed=3)
+    ki, vi = rnd(B, 16, C, seed=4), rnd(B, 16, C, seed=5)
+    out = lib.attention(q, kt, vt, heads=H)
+    out = lib.attention(q, ki, vi, heads=H, accumulate=True, out=out)
+    ref = r16(r16(_attn_ref(q, kt, vt, H, 0.125)) + r16(_attn_ref(q, ki, vi, H, 0.125)))
+    close(out, ref, tol=3e-3)
+
+
+@pytest.mark.parametrize("B,HW,C0,C1,silu,eps", [(2, 768, 1280, 0, 1, 1e-5), (2, 3072, 320, 0, 0, 1e-6),
+                                                 (3, 500, 640, 320, 1, 1e-5), (2, 768, 1280, 640, 1, 1e-5),
+                                                 (1, 64, 2560, 0, 1, 1e-5), (4, 12288, 320, 0, 1, 1e-5)])
+def test_groupnorm(lib, B, HW, C0, C1, silu, eps):
+    x0 = rnd(B, HW, C0, seed=1) + 0.5
+    x1 = rnd(B, HW, C1, seed=2) * 2 if C1 else None
+    C = C0 + C1
+    gamma, beta = rnd(C, seed=3), rnd(C, seed=4)
+    out = lib.groupnorm(x0, gamma, beta, eps, silu, x1=x1)
+    x = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(x.float().transpose(1, 2), 32, gamma.float(), beta.float(), eps).transpose(1, 2)
+    if silu:
+        ref = F.silu(ref)
+    close(out, ref)
+
+
+@pytest.mark.parametrize("rows,C", [(768, 1280), (1000, 640), (33, 2048), (16, 1280)])
+def test_layernorm(lib, rows, C):
+    x = rnd(rows, C, seed=1) * 3 + 1
+    g, b = rnd(C, seed=2), rnd(C, seed=3)
+    out = lib.layernorm(x, g, b, 1e-5)
+    close(out, F.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5))
+
+
+def test_layout_and_samplers(lib):
+    B, C, H, W = 2, 4, 16, 12
+    lat = rnd(B, C, H, W, seed=1)
+    dst = torch.zeros(2 * B, H, W, 64, dtype=torch.float16, device="cuda")
+    lib.nchw_to_nhwc(lat, dst, c_off=0)
+    extra = rnd(2 * B, 9, H, W, seed=2)
+    lib.nchw_to_nhwc(extra, dst, c_off=4)
+    ref = torch.cat([torch.cat([lat, lat]), extra], 1).permute(0, 2, 3, 1)
+    assert torch.equal(dst[..., :13], ref) and dst[..., 13:].abs().max() == 0
+    back = lib.nhwc_to_nchw(dst, 13)
+    assert torch.equal(back, ref.permute(0, 3, 1, 2))
+    x = rnd(2, 8, 6, 64, seed=3)
+    up = lib.upsample2x(x)
+    assert torch.equal(up, F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")
+                       .permute(0, 2, 3, 1).half())
+
+
+def test_downsample_conv_via_im2col(lib):
+    B, H, W, C, Cout = 2, 16, 12, 128, 128
+    x = rnd(B, H, W, C, seed=1)
+    w = rnd(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=2)
+    bias = rnd(Cout, seed=3)
+    cols = lib.im2col3x3_s2(x)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()
+    out = lib.gemm(cols, wk, bias=bias).view(B, H // 2, W // 2, Cout)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    close(out, ref)
+
+
+def test_timestep_embedding_and_skinny_linear(lib):
+    t = torch.tensor([967.0], device="cuda")
+    emb = lib.timestep_embedding(t, 320, rows_repeat=4)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    arg = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(arg), torch.sin(arg)], -1).expand(4, -1)
+    close(emb, ref, tol=1e-3)
+    x = rnd(4, 320, seed=1)
+    w1, b1 = rnd(1280, 320, scale=320 ** -0.5, seed=2), rnd(1280, seed=3)
+    add = rnd(4, 1280, seed=4)
+    y = lib.skinny_linear(x, w1, b1, out_silu=True, addend=add)
+    ref = r16(r16(F.silu(r16(x.float() @ w1.float().t() + b1.float()))) + add.float())
+    close(y, ref)
+    y2 = lib.skinny_linear(y, rnd(3000, 1280, scale=1280 ** -0.5, seed=5), None, in_silu=True)
+    ref2 = r16(r16(F.silu(y.float())) @ rnd(3000, 1280, scale=1280 ** -0.5, seed=5).float().t())
+    close(y2, ref2)
+
+
+def test_cfg_ddpm_step(lib):
+    B, C, H, W = 2, 4, 16, 12
+    eps = rnd(2 * B, H, W, 16, seed=1)
+    lat, noise = rnd(B, C, H, W, seed=2), rnd(B, C, H, W, seed=3)
+    coef = torch.tensor([2.0, 0.83, 1.0 / 0.55, 0.31, 0.68, 0.12], device="cuda")
+    out = lib.cfg_ddpm_step(eps, lat, noise, coef)
+    e = eps[..., :C].permute(0, 3, 1, 2).float()
+    u, t = e[:B], e[B:]
+    g = r16(u + r16(2.0 * r16(t - u)))
+    x = lat.float()
+    x0 = r16(r16(x - r16(coef[1] * g)) * coef[2])
+    prev = r16(r16(coef[3] * x0) + r16(coef[4] * x))
+    ref = r16(prev + r16(coef[5] * noise.float()))
+    close(out, ref, tol=1e-3)
