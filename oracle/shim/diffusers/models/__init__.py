@@ -1,0 +1,3 @@
+from .._stubs import stub_getattr
+
+__getattr__ = stub_getattr(__name__)
