@@ -1,0 +1,110 @@
+"""The denoising hot loop of IDM-VTON on the B200 engine (src/tryon_pipeline.py:1765-1866).
+
+Per step the reference runs the garment UNet (batch Bg), zero-pads its 70 features for the CFG-uncond half, runs the
+try-on UNet (batch 2B), applies CFG and the DDPM update. Here one step is a fixed launch sequence over static buffers:
+  latents -> [NCHW->NHWC scatter into the 13(+pad)-channel input] -> garment UNet -> try-on UNet (garment K/V streamed
+  as a second attention segment, uncond half in closed form) -> fused CFG+DDPM
+captured once in a CUDA graph and replayed per step; step-invariant work (cross-attention K/V of text / IP tokens,
+aug_emb, the static input channels) is hoisted to prepare().
+"""
+import torch
+
+from .engine import CIN_PAD, UNetEngine
+
+
+class TryOnDenoiser:
+    def __init__(self, tryon: UNetEngine, garment: UNetEngine):
+        self.tryon = tryon
+        self.garment = garment
+        self.L = tryon.L
+        self.device = tryon.device
+        self._graph = None
+
+    # -------------------------------------------------------------------------------------------
+    def prepare(self, latents, mask, masked_image_latents, pose_latents, cloth_latents, prompt_embeds,
+                add_text_embeds, add_time_ids, image_embeds, text_embeds_cloth, guidance_scale=2.0, do_cfg=True):
+        """All tensors on the device. latents [B,4,h,w]; mask [Bt,1,h,w], masked_image_latents / pose_latents
+        [Bt,4,h,w], prompt_embeds [Bt,77,X], add_text_embeds [Bt,P], add_time_ids [Bt,6], image_embeds [Bt,16,X]
+        with Bt = 2B under CFG ([uncond ; cond] order, src/tryon_pipeline.py:1711-1714); cloth_latents [Bg,4,h,w],
+        text_embeds_cloth [Bg,77,X]."""
+        L = self.L
+        f16 = torch.float16
+        B, _, h, w = latents.shape
+        Bt = 2 * B if do_cfg else B
+        Bg = cloth_latents.shape[0]
+        self.B, self.Bt, self.Bg, self.h, self.w = B, Bt, Bg, h, w
+        self.do_cfg = do_cfg
+        self.guidance_scale = float(guidance_scale)
+        dev = self.device
+        self._graph = None
+        self.latents = latents.to(dev, f16).contiguous().clone()
+        self.latents_next = torch.empty_like(self.latents)
+        self.noise = torch.zeros_like(self.latents)
+        self.x_t = torch.zeros((Bt, h, w, CIN_PAD), dtype=f16, device=dev)
+        L.nchw_to_nhwc(mask.to(dev, f16).contiguous(), self.x_t, c_off=4)
+        L.nchw_to_nhwc(masked_image_latents.to(dev, f16).contiguous(), self.x_t, c_off=5)
+        L.nchw_to_nhwc(pose_latents.to(dev, f16).contiguous(), self.x_t, c_off=9)
+        self.x_g = torch.zeros((Bg, h, w, CIN_PAD), dtype=f16, device=dev)
+        L.nchw_to_nhwc(cloth_latents.to(dev, f16).contiguous(), self.x_g, c_off=0)
+        self.ctx_t = self.tryon.encode_context(prompt_embeds.to(dev, f16), image_embeds.to(dev, f16))
+        self.ctx_g = self.garment.encode_context(text_embeds_cloth.to(dev, f16))
+        self.aug = self.tryon.aug_embedding(add_text_embeds.to(dev, f16), add_time_ids.to(dev))
+        self.t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.coef = torch.zeros(6, dtype=torch.float32, device=dev)
+        self.eps = None
+
+    def set_step_tables(self, scheduler, timesteps):
+        """Uploads the per-step scalars: t and {gs, sqrt(1-abar), 1/sqrt(abar), c0, c1, sigma}."""
+        rows = []
+        for t in timesteps:
+            rows.append([self.guidance_scale, *scheduler.step_coefficients(int(t))])
+        self.coef_table = torch.tensor(rows, dtype=torch.float32, device=self.device)
+        self.t_table = torch.tensor([float(int(t)) for t in timesteps], dtype=torch.float32, device=self.device)
+
+    # -------------------------------------------------------------------------------------------
+    def _launch_step(self):
+        """The launch sequence of one denoise step over the static buffers (graph-capturable)."""
+        L = self.L
+        L.nchw_to_nhwc(self.latents, self.x_t, c_off=0)          # CFG duplication + channel concat as offsets
+        feats = []
+        temb_g = self.garment.time_embedding(self.t_dev, self.Bg)
+        self.garment.forward(self.x_g, temb_g, self.ctx_g, collect=feats)
+        temb_t = self.tryon.time_embedding(self.t_dev, self.Bt, self.aug)
+        gf = feats
+        n_persons = self.B if self.do_cfg else 0
+        self.eps = self.tryon.forward(self.x_t, temb_t, self.ctx_t, gfeats=gf, n_persons=n_persons)
+        L.cfg_ddpm_step(self.eps, self.latents, self.noise, self.coef, do_cfg=self.do_cfg, out=self.latents_next)
+        self.latents.copy_(self.latents_next)
+
+    def capture(self):
+        """Capture one step into a CUDA graph (after a warm-up launch on a side stream)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        keep = self.latents.clone()
+        with torch.cuda.stream(s):
+            self._launch_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_step()
+        self.latents.copy_(keep)
+        self._graph = g
+
+    def step(self, i, noise=None, use_graph=True):
+        """Runs denoise step i (tables from set_step_tables). noise: [B,4,h,w] fp16 variance noise or None."""
+        self.t_dev.copy_(self.t_table[i:i + 1])
+        self.coef.copy_(self.coef_table[i])
+        if noise is not None:
+            self.noise.copy_(noise)
+        else:
+            self.noise.zero_()
+        if use_graph:
+            if self._graph is None:
+                self.capture()
+                self.t_dev.copy_(self.t_table[i:i + 1])
+                self.coef.copy_(self.coef_table[i])
+            self._graph.replay()
+        else:
+            self._launch_step()
+        return self.latents

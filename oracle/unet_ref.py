@@ -56,7 +56,9 @@ def tiny_config(kind):
     base.update(block_out_channels=(64, 128, 256), transformer_layers_per_block=(1, 1, 2), num_heads=(1, 2, 4),
                 cross_attention_dim=256, addition_time_embed_dim=64, projection_class_embeddings_input_dim=6 * 64 + 128)
     if kind == "tryon":
-        base["resampler"] = dict(dim=128, depth=2, dim_head=64, heads=2, num_queries=16, embedding_dim=192,
+        # the reference hard-codes the Resampler geometry (src/unet_hacked_tryon.py:476-485); only the CLIP width
+        # (encoder_hid_dim) and the output width (cross_attention_dim) follow the config
+        base["resampler"] = dict(dim=1280, depth=4, dim_head=64, heads=20, num_queries=16, embedding_dim=192,
                                  output_dim=256, ff_mult=4)
     return base
 
