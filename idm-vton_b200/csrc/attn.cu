@@ -322,6 +322,7 @@ int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long
   }
   dim3 grid((Nq + 127) / 128, H, B);
   attn_kernel<<<grid, 192, AT_SMEM_TOTAL, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }

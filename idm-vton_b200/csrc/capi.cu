@@ -6,7 +6,7 @@
 namespace vton {
 int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
                   int K, const void* bias, const void* residual, long long ldr, const void* rowvec, long long ld_rowvec,
-                  int rows_per_sample, int geglu, int force_bn, cudaStream_t stream);
+                  int rows_per_sample, int flags, int force_bn, cudaStream_t stream);
 int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                  const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
@@ -37,12 +37,13 @@ extern "C" {
 
 int b200vton_version(void) { return 100; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
+long long b200vton_launch_count(void) { return vton::launch_count(); }
 
 int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N,
                       int K, const void* bias, const void* residual, int64_t ldr, const void* rowvec,
-                      int64_t ld_rowvec, int rows_per_sample, int geglu, int force_bn, void* stream) {
+                      int64_t ld_rowvec, int rows_per_sample, int flags, int force_bn, void* stream) {
   return vton::gemm_f16_impl(A, lda, W, ldw, out, ldo, M, N, K, bias, residual, ldr, rowvec, ld_rowvec,
-                             rows_per_sample, geglu, force_bn, S(stream));
+                             rows_per_sample, flags, force_bn, S(stream));
 }
 
 int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int Cin, const void* w, int Cout,

@@ -37,6 +37,7 @@ int nchw_to_nhwc_impl(const void* src, int Bs, int Cs, int H, int W, void* dst, 
   const long long total = static_cast<long long>(Bd) * H * W;
   nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const __half*>(src), Bs, Cs, H * W, static_cast<__half*>(dst), Bd, ldc, c_off);
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -46,6 +47,7 @@ int nhwc_to_nchw_impl(const void* src, int B, int C, int H, int W, int ldc, void
   const long long total = static_cast<long long>(B) * C * H * W;
   nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const __half*>(src), B, C, H * W, ldc, static_cast<__half*>(dst));
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -72,6 +74,7 @@ int upsample2x_impl(const void* src, int B, int H, int W, int C, void* dst, cuda
   const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
   upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const uint4*>(src), B, H, W, C / 8, static_cast<uint4*>(dst));
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -105,6 +108,7 @@ int im2col_s2_impl(const void* src, int B, int H, int W, int C, void* dst, cudaS
   const long long total = static_cast<long long>(B) * Ho * Wo * 9 * (C / 8);
   im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const uint4*>(src), B, H, W, C / 8, Ho, Wo, static_cast<uint4*>(dst));
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -132,6 +136,7 @@ int timestep_embed_impl(const void* values, int n, int dim, int rows_repeat, voi
   const int total = n * rows_repeat * (dim / 2);
   timestep_embed_kernel<<<(total + 127) / 128, 128, 0, stream>>>(static_cast<const float*>(values), n, dim,
                                                                   static_cast<__half*>(out), rows_repeat);
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -215,6 +220,7 @@ int skinny_linear_impl(const void* x, int ldx, int M, int K, const void* W, long
   skinny_linear_kernel<<<cdiv(N, 8), 256, smem, stream>>>(
       static_cast<const __half*>(x), ldx, M, K, static_cast<const __half*>(W), ldw, N, static_cast<const __half*>(bias),
       in_silu, out_silu, static_cast<const __half*>(addend), ld_add, static_cast<__half*>(out), ldo);
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -258,6 +264,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
   cfg_ddpm_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       static_cast<const __half*>(eps), ldc, B, C, H * W, static_cast<const __half*>(latents),
       static_cast<const __half*>(noise), static_cast<const float*>(coef), do_cfg, static_cast<__half*>(out));
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }

@@ -37,6 +37,7 @@ struct GemmParams {
   int cin_slabs;  // Cin / 64
   int cout;       // rows per tap in the packed weight
   int n_tiles;
+  int act_gelu;  // v = fp16(gelu_erf(fp16(acc + bias))) before the later epilogue terms (Resampler FeedForward)
 };
 
 constexpr int BM = 128;
@@ -243,6 +244,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[2 * j + 1] += a.y;
             }
           }
+          if (p.act_gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
+          }
           if (p.rowvec) {
             const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
             const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
@@ -314,6 +319,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     configured = true;
   }
   kern<<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmS0, tmS1, tmBs, p);
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -350,7 +356,8 @@ static int dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMa
 
 int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo, int M, int N,
                   int K, const void* bias, const void* residual, long long ldr, const void* rowvec, long long ld_rowvec,
-                  int rows_per_sample, int geglu, int force_bn, cudaStream_t stream) {
+                  int rows_per_sample, int flags, int force_bn, cudaStream_t stream) {
+  const int geglu = flags & 1;
   VTON_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   VTON_CHECK_ARG(K % 64 == 0, "gemm: K=%d must be a multiple of 64", K);
   VTON_CHECK_ARG(N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "gemm: N/lda/ldw/ldo must be multiples of 8");
@@ -383,6 +390,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   p.ld_rowvec = static_cast<int>(ld_rowvec);
   p.rows_per_sample = rows_per_sample;
   p.slabs_main = K / 64;
+  p.act_gelu = (flags & 2) ? 1 : 0;
   return dispatch(bn, geglu != 0, tmA, tmB, tmA, tmA, tmB, p, cdiv(M, BM), stream);
 }
 

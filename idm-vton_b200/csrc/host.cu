@@ -3,6 +3,7 @@
 // dependency on libcuda and loads on a machine without a driver (the CPU build/"symbols export" check).
 #include "host.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace vton {
@@ -16,6 +17,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -39,4 +39,8 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Number of kernels this library has launched (or recorded into a capturing stream) since load.
+void count_launch(int n = 1);
+long long launch_count();
+
 }  // namespace vton

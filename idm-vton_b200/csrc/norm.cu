@@ -159,6 +159,7 @@ int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW
   gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<const double*>(stats_ws),
                                                    static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                                                    eps, silu, static_cast<__half*>(out));
+  count_launch(2);
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -239,6 +240,7 @@ int layernorm_impl(const void* x, long long ldx, int rows, int C, const void* ga
   layernorm_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(static_cast<const __half*>(x), ldx, rows, C,
                                                      static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                                                      eps, static_cast<__half*>(out), ldo);
+  count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
 }

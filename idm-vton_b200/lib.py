@@ -52,12 +52,18 @@ def load(build_if_missing=True):
     lib = ctypes.CDLL(LIB_PATH)
     lib.b200vton_version.restype = _i
     lib.b200vton_last_error.restype = _c.c_char_p
+    lib.b200vton_launch_count.restype = _c.c_longlong
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = _i
     _lib = lib
     return lib
+
+
+def launch_count():
+    """Kernels launched (or captured) by libb200vton.so since load."""
+    return int(load().b200vton_launch_count())
 
 
 def _check(rc, name):
@@ -84,7 +90,7 @@ def _f16(t, name):
 # ------------------------------------------------------------------------------------------------
 # op wrappers
 # ------------------------------------------------------------------------------------------------
-def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=False, out=None, force_bn=0):
+def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=False, gelu=False, out=None, force_bn=0):
     """out[M,N] = epi(a[M,K] @ w[N,K]^T). a / residual / out may be row-strided 2-D views (last dim contiguous)."""
     lib = load()
     _f16(a, "a"); _f16(w, "w")
@@ -99,7 +105,7 @@ def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=F
         assert residual.shape == (M, n_out) and residual.stride(1) == 1
     rc = lib.b200vton_gemm_f16(_p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
                                _p(residual), residual.stride(0) if residual is not None else 0, _p(rowvec),
-                               rowvec.stride(0) if rowvec is not None else 0, rows_per_sample, int(geglu), force_bn,
+                               rowvec.stride(0) if rowvec is not None else 0, rows_per_sample, int(geglu) | (2 if gelu else 0), force_bn,
                                _stream())
     _check(rc, "b200vton_gemm_f16")
     return out

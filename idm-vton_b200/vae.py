@@ -1,0 +1,252 @@
+"""AutoencoderKL (SDXL VAE) and VaeImageProcessor stand-ins in plain PyTorch — HOST-SIDE PLUMBING, not the hot path.
+
+The reference pipeline receives a diffusers `AutoencoderKL` as a component (src/tryon_pipeline.py:387-401) and calls
+`vae.encode(x).latent_dist.sample(generator)`, `vae.decode(z, return_dict=False)[0]`, `vae.config.{scaling_factor,
+force_upcast,latent_channels,block_out_channels}` (:911-932,1646,1868-1880). diffusers is not installable in this image, so
+this module supplies an architecture-compatible VAE (same parameter names as diffusers 0.25.0's AutoencoderKL, restated
+from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): it is
+executed by PyTorch/cuDNN here and will move onto the engine's conv / GroupNorm kernels after the denoise loop.
+"""
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class _Resnet(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(32, cin, eps=1e-6)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2 = nn.GroupNorm(32, cout, eps=1e-6)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+
+    def forward(self, x):
+        h = self.conv1(F.silu(self.norm1(x)))
+        h = self.conv2(F.silu(self.norm2(h)))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h
+
+
+class _Attn(nn.Module):
+    """Single-head spatial self-attention of the VAE mid block (diffusers Attention with group_norm, bias=True)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.group_norm = nn.GroupNorm(32, c, eps=1e-6)
+        self.to_q, self.to_k, self.to_v = nn.Linear(c, c), nn.Linear(c, c), nn.Linear(c, c)
+        self.to_out = nn.ModuleList([nn.Linear(c, c), nn.Dropout(0.0)])
+
+    def forward(self, x):
+        b, c, h, w = x.shape
+        t = self.group_norm(x).view(b, c, h * w).transpose(1, 2)
+        q, k, v = self.to_q(t), self.to_k(t), self.to_v(t)
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        o = self.to_out[0](o)
+        return x + o.transpose(1, 2).reshape(b, c, h, w)
+
+
+class _Mid(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.attentions = nn.ModuleList([_Attn(c)])
+        self.resnets = nn.ModuleList([_Resnet(c, c), _Resnet(c, c)])
+
+    def forward(self, x):
+        return self.resnets[1](self.attentions[0](self.resnets[0](x)))
+
+
+class _Down(nn.Module):
+    def __init__(self, cin, cout, layers, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([_Resnet(cin if i == 0 else cout, cout) for i in range(layers)])
+        self.downsamplers = None
+        if add_down:
+            d = nn.Module()
+            d.conv = nn.Conv2d(cout, cout, 3, stride=2, padding=0)
+            self.downsamplers = nn.ModuleList([d])
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0].conv(F.pad(x, (0, 1, 0, 1)))
+        return x
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout, layers, add_up):
+        super().__init__()
+        self.resnets = nn.ModuleList([_Resnet(cin if i == 0 else cout, cout) for i in range(layers)])
+        self.upsamplers = None
+        if add_up:
+            u = nn.Module()
+            u.conv = nn.Conv2d(cout, cout, 3, padding=1)
+            self.upsamplers = nn.ModuleList([u])
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0].conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+        return x
+
+
+class _Encoder(nn.Module):
+    def __init__(self, cin, ch, layers, latent):
+        super().__init__()
+        self.conv_in = nn.Conv2d(cin, ch[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList(
+            [_Down(ch[max(i - 1, 0)], c, layers, i < len(ch) - 1) for i, c in enumerate(ch)])
+        self.mid_block = _Mid(ch[-1])
+        self.conv_norm_out = nn.GroupNorm(32, ch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[-1], 2 * latent, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for d in self.down_blocks:
+            x = d(x)
+        x = self.mid_block(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+class _Decoder(nn.Module):
+    def __init__(self, cout, ch, layers, latent):
+        super().__init__()
+        rch = list(reversed(ch))
+        self.conv_in = nn.Conv2d(latent, rch[0], 3, padding=1)
+        self.mid_block = _Mid(rch[0])
+        self.up_blocks = nn.ModuleList(
+            [_Up(rch[max(i - 1, 0)], c, layers + 1, i < len(ch) - 1) for i, c in enumerate(rch)])
+        self.conv_norm_out = nn.GroupNorm(32, rch[-1], eps=1e-6)
+        self.conv_out = nn.Conv2d(rch[-1], cout, 3, padding=1)
+
+    def forward(self, z):
+        x = self.mid_block(self.conv_in(z))
+        for u in self.up_blocks:
+            x = u(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+class DiagonalGaussianDistribution:
+    def __init__(self, parameters):
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+
+class AutoencoderKL(nn.Module):
+    """SDXL VAE geometry by default (block_out_channels 128/256/512/512, 4 latent channels, scaling 0.13025)."""
+
+    def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 latent_channels=4, scaling_factor=0.13025, force_upcast=True):
+        super().__init__()
+        ch = tuple(block_out_channels)
+        self.encoder = _Encoder(in_channels, ch, layers_per_block, latent_channels)
+        self.decoder = _Decoder(out_channels, ch, layers_per_block, latent_channels)
+        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
+        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        self.config = types.SimpleNamespace(in_channels=in_channels, out_channels=out_channels, block_out_channels=ch,
+                                            layers_per_block=layers_per_block, latent_channels=latent_channels,
+                                            scaling_factor=scaling_factor, force_upcast=force_upcast)
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def encode(self, x, return_dict=True):
+        dist = DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))
+        return types.SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
+
+    def decode(self, z, return_dict=True, generator=None):
+        img = self.decoder(self.post_quant_conv(z))
+        return types.SimpleNamespace(sample=img) if return_dict else (img,)
+
+    def enable_slicing(self):
+        pass
+
+    disable_slicing = enable_tiling = disable_tiling = enable_slicing
+
+
+class VaeImageProcessor:
+    """The subset of diffusers' VaeImageProcessor the pipeline uses (src/tryon_pipeline.py:418-421,1588-1602,1885):
+    resize to (height, width), [0,1] -> [-1,1] normalisation, optional grayscale + binarisation for masks; tensors,
+    numpy arrays and PIL images are accepted; postprocess to "pil" / "np" / "pt" / "latent"."""
+
+    def __init__(self, vae_scale_factor=8, do_resize=True, do_normalize=True, do_binarize=False,
+                 do_convert_grayscale=False):
+        self.vae_scale_factor = vae_scale_factor
+        self.do_resize, self.do_normalize = do_resize, do_normalize
+        self.do_binarize, self.do_convert_grayscale = do_binarize, do_convert_grayscale
+
+    def _to_tensor(self, image):
+        import PIL.Image
+        if isinstance(image, torch.Tensor):
+            t = image
+            if t.ndim == 3:
+                t = t[None] if not self.do_convert_grayscale or t.shape[0] in (1, 3) else t[:, None]
+            return t.float(), True
+        if isinstance(image, PIL.Image.Image):
+            image = [image]
+        if isinstance(image, (list, tuple)) and isinstance(image[0], PIL.Image.Image):
+            arrs = []
+            for im in image:
+                im = im.convert("L") if self.do_convert_grayscale else im.convert("RGB")
+                a = np.asarray(im, dtype=np.float32) / 255.0
+                arrs.append(a[..., None] if a.ndim == 2 else a)
+            return torch.from_numpy(np.stack(arrs)).permute(0, 3, 1, 2), False
+        if isinstance(image, np.ndarray):
+            a = image[None] if image.ndim == 3 else image
+            return torch.from_numpy(a.astype(np.float32)).permute(0, 3, 1, 2), False
+        if isinstance(image, (list, tuple)) and isinstance(image[0], torch.Tensor):
+            return torch.stack([i if i.ndim == 3 else i[0] for i in image]).float(), True
+        raise ValueError(f"unsupported image input type {type(image)}")
+
+    def preprocess(self, image, height=None, width=None, resize_mode="default", crops_coords=None):
+        if crops_coords is not None or resize_mode != "default":
+            raise NotImplementedError("padding_mask_crop is not on the IDM-VTON inference path")
+        t, was_tensor = self._to_tensor(image)
+        if t.shape[1] == 4 and not self.do_convert_grayscale:   # already latents
+            return t
+        if self.do_convert_grayscale and t.shape[1] == 3:
+            t = (0.299 * t[:, 0:1] + 0.587 * t[:, 1:2] + 0.114 * t[:, 2:3])
+        if self.do_resize and height is not None and (t.shape[-2] != height or t.shape[-1] != width):
+            t = F.interpolate(t, size=(height, width))
+        do_norm = self.do_normalize
+        if was_tensor and do_norm and t.min() < 0:
+            do_norm = False          # diffusers: tensors already in [-1, 1] are not normalised again
+        if do_norm:
+            t = 2.0 * t - 1.0
+        if self.do_binarize:
+            t = (t >= 0.5).to(t.dtype)
+        return t
+
+    def postprocess(self, image, output_type="pil", do_denormalize=None):
+        if output_type == "latent":
+            return image
+        if not isinstance(image, torch.Tensor):
+            return image
+        img = (image.float() / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return img
+        arr = img.cpu().permute(0, 2, 3, 1).numpy()
+        if output_type == "np":
+            return arr
+        import PIL.Image
+        arr = (arr * 255).round().astype("uint8")
+        return [PIL.Image.fromarray(a.squeeze()) if a.shape[-1] == 1 else PIL.Image.fromarray(a) for a in arr]

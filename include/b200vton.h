@@ -25,17 +25,20 @@ extern "C" {
 
 int b200vton_version(void);
 const char* b200vton_last_error(void);
+/* kernels launched (or recorded into a capturing stream) by this library since it was loaded */
+long long b200vton_launch_count(void);
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear on the hot path — attn to_q/to_k/to_v/to_out
  * (ip_adapter/attention_processor.py:240-268), Transformer2DModel.proj_in/proj_out
  * (src/transformerhacked_tryon.py:331-345,410-427), FeedForward GEGLU / net.2 (src/attentionhacked_tryon.py:621-679).
  * epi: v = fp16(acc + bias[n]); v = fp16(v + rowvec[m / rows_per_sample, n]); v = fp16(v + residual[m, n]).
- * geglu != 0: W/bias rows are tile-interleaved [value | gate] (see engine.pack_geglu) and
+ * flags & 1 (GEGLU): W/bias rows are tile-interleaved [value | gate] (see engine.pack_geglu) and
  *             out[M, N/2] = fp16(value) * fp16(gelu_erf(fp16(gate))).
+ * flags & 2 (GELU): v = fp16(gelu_erf(fp16(acc + bias))) before the rowvec / residual terms (ip_adapter/resampler.py:13-20).
  * K % 64 == 0; N, lda, ldw, ldo % 8 == 0. force_bn: 0 = auto tile width, else 64/128/160/256. */
 int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N,
                       int K, const void* bias, const void* residual, int64_t ldr, const void* rowvec,
-                      int64_t ld_rowvec, int rows_per_sample, int geglu, int force_bn, void* stream);
+                      int64_t ld_rowvec, int rows_per_sample, int flags, int force_bn, void* stream);
 
 /* NHWC 3x3 convolution, stride 1, pad 1, as implicit GEMM: diffusers ResnetBlock2D.conv1/conv2 (+conv_shortcut),
  * conv_in / conv_out (src/unet_hacked_tryon.py:416,755,1245,1386), the conv of Upsample2D.

@@ -26,7 +26,7 @@ def _to(d, device, dtype):
 
 
 def _err(a, b):
-    a, b = a.float(), b.float()
+    a, b = a.float().cpu(), b.float().cpu()
     return (a - b).abs().max().item() / max(1.0, b.abs().max().item())
 
 
