@@ -169,10 +169,15 @@ def synth_request(cfg_t, cfg_g, batch, h, w, seed, device):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------
+SAMPLE_H, SAMPLE_W = 32, 24     # latent size of the bounded CPU sample (256x192 px = 1/16 of the 768x1024 pixels)
+
+
 def cpu_reference_sample(steps, warmup, sd_src=None, log=None):
-    """Times `steps` bounded samples of the reference path (oracle/unet_ref.py, CPU fp32, all host threads).
-    Sample = ONE denoise step of the config-2 workload for ONE request (768x1024, CFG: try-on batch 2 + garment batch 1);
-    a 30-step image costs 30 such samples, so images/sec = 1 / (30 * t_sample)  [extrapolated]."""
+    """Times `steps` bounded samples of the reference path (oracle/unet_ref.py + loop_ref.py, CPU fp32, all host
+    threads). Sample = ONE denoise step for ONE request (garment UNet batch 1 + try-on UNet batch 2 under CFG + CFG +
+    DDPM update) with the full SDXL-size UNets on a 256x192-pixel crop of the 768x1024 workload (a full-resolution
+    step takes minutes on the host). images/sec is extrapolated by the algorithmic-FLOP ratio:
+        t_image = 30 * t_sample * FLOPs(768x1024 step) / FLOPs(sample step)."""
     from oracle import loop_ref as LR
     from oracle import unet_ref as R
     cores = os.cpu_count() or 1
@@ -199,8 +204,8 @@ def cpu_reference_sample(steps, warmup, sd_src=None, log=None):
         sd_t, sd_g = mk(cfg_t, 11), mk(cfg_g, 22)
     if log:
         log(f"reference arm: host weights ready in {time.time() - t0:.1f}s, {cores} threads")
-    h, w = HEIGHT // 8, WIDTH // 8
-    inp = LR.synth_loop_inputs(cfg_t, cfg_g, 1, h, w, seed=0)
+    inp = LR.synth_loop_inputs(cfg_t, cfg_g, 1, SAMPLE_H, SAMPLE_W, seed=0)
+    ratio = step_flops(cfg_t, cfg_g, HEIGHT // 8, WIDTH // 8, 1, 1) / step_flops(cfg_t, cfg_g, SAMPLE_H, SAMPLE_W, 1, 1)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -212,9 +217,11 @@ def cpu_reference_sample(steps, warmup, sd_src=None, log=None):
             if log:
                 log(f"reference arm: sample {i} took {dt:.2f}s")
     t_sample = sum(times) / len(times)
-    return dict(value=1.0 / (STEPS_DENOISE * t_sample), t_sample=t_sample, cores=cores, times=times,
-                sample="1 denoise step (garment UNet batch 1 + try-on UNet batch 2, CFG) at 768x1024 per sample; "
-                       "images/sec = 1/(30 * t_sample), linearly extrapolated; oracle port (PyTorch CPU fp32)")
+    return dict(value=1.0 / (STEPS_DENOISE * t_sample * ratio), t_sample=t_sample, cores=cores, times=times, flop_ratio=ratio,
+                sample=f"1 denoise step (garment UNet batch 1 + try-on UNet batch 2, CFG, full SDXL-size weights) on a "
+                       f"256x192 px crop (latent {SAMPLE_H}x{SAMPLE_W}); images/sec = 1/(30 * t_sample * {ratio:.2f}) where "
+                       f"{ratio:.2f} = algorithmic FLOPs of a 768x1024 step / FLOPs of the sample; oracle port "
+                       "(PyTorch CPU fp32, all host threads); extrapolated")
 
 
 def run_reference(args, rank, world):

@@ -28,8 +28,10 @@ __device__ __forceinline__ uint4 gn_load(const GnSrc& s, long long row, int v) {
   return *reinterpret_cast<const uint4*>(s.x1 + row * s.C1 + (c - s.C0));
 }
 
-// stats[b][g][0] = sum, [1] = sum of squares (double, pre-zeroed)
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int rows_per_cta, double* stats) {
+// Deterministic two-stage statistics (no atomics, so a CUDA-graph replay is bit-identical to eager launches):
+//   stage 1: CTA (chunk, b) reduces its rows -> partial[b][chunk][g] = {sum, sum of squares} (fixed reduction order)
+//   stage 2: the apply kernel's first 32 threads sum the chunk partials of their group in order (double).
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int rows_per_cta, double* partial) {
   const int C = src.C0 + src.C1;
   const int V = C / 8;
   const int cpg = C / GN_GROUPS;
@@ -37,12 +39,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
   const int b = blockIdx.y;
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(HW, r_begin + rows_per_cta);
-  __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
-  if (threadIdx.x < GN_GROUPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
+  __shared__ float ps[GN_THREADS * 8];  // [row_lane][C] partial sums
+  __shared__ float pq[GN_THREADS * 8];  // [row_lane][C] partial sums of squares
   const int v = threadIdx.x % V;
   const int rl = threadIdx.x / V;
   if (rl < row_lanes) {
@@ -61,33 +59,37 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
         sq[2 * j + 1] += f.y * f.y;
       }
     }
-    // fold the 8 channels into their groups (a vector may straddle two groups)
-    int g_prev = (v * 8) / cpg;
-    float acc_s = 0.f, acc_q = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], acc_s);
-        atomicAdd(&s_sq[g_prev], acc_q);
-        acc_s = acc_q = 0.f;
-        g_prev = g;
-      }
-      acc_s += sum[j];
-      acc_q += sq[j];
+      ps[rl * C + v * 8 + j] = sum[j];
+      pq[rl * C + v * 8 + j] = sq[j];
     }
-    atomicAdd(&s_sum[g_prev], acc_s);
-    atomicAdd(&s_sq[g_prev], acc_q);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {  // per-channel totals, fixed order over row lanes
+    float a = 0.f, q = 0.f;
+    for (int l = 0; l < row_lanes; ++l) {
+      a += ps[l * C + c];
+      q += pq[l * C + c];
+    }
+    ps[c] = a;
+    pq[c] = q;
   }
   __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
-    atomicAdd(&stats[(static_cast<long long>(b) * GN_GROUPS + threadIdx.x) * 2 + 0], static_cast<double>(s_sum[threadIdx.x]));
-    atomicAdd(&stats[(static_cast<long long>(b) * GN_GROUPS + threadIdx.x) * 2 + 1], static_cast<double>(s_sq[threadIdx.x]));
+    double a = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) {
+      a += static_cast<double>(ps[threadIdx.x * cpg + i]);
+      q += static_cast<double>(pq[threadIdx.x * cpg + i]);
+    }
+    double* dst = partial + ((static_cast<long long>(b) * gridDim.x + blockIdx.x) * GN_GROUPS + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = q;
   }
 }
 
 __global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* stats, const __half* gamma, const __half* beta,
+gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* partial, const __half* gamma, const __half* beta,
                 float eps, int silu, __half* out) {
   const int C = src.C0 + src.C1;
   const int V = C / 8;
@@ -98,23 +100,32 @@ gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* stats, const 
   const int r_end = min(HW, r_begin + rows_per_cta);
   const int v = threadIdx.x % V;
   const int rl = threadIdx.x / V;
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  if (threadIdx.x < GN_GROUPS) {
+    double a = 0.0, q = 0.0;
+    for (int ch = 0; ch < static_cast<int>(gridDim.x); ++ch) {
+      const double* p = partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + threadIdx.x) * 2;
+      a += p[0];
+      q += p[1];
+    }
+    const double n = static_cast<double>(cpg) * HW;
+    const double mean = a / n;
+    double var = q / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+  }
+  __syncthreads();
   if (rl >= row_lanes) return;
   float sc[8], sh[8];
-  const double n = static_cast<double>(cpg) * HW;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = v * 8 + j;
     const int g = c / cpg;
-    const double s = stats[(static_cast<long long>(b) * GN_GROUPS + g) * 2 + 0];
-    const double q = stats[(static_cast<long long>(b) * GN_GROUPS + g) * 2 + 1];
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    const float rstd = rsqrtf(static_cast<float>(var) + eps);
     const float gm = gamma ? h2f(gamma[c]) : 1.f;
     const float bt = beta ? h2f(beta[c]) : 0.f;
-    sc[j] = rstd * gm;
-    sh[j] = bt - static_cast<float>(mean) * sc[j];
+    sc[j] = s_rstd[g] * gm;
+    sh[j] = bt - s_mean[g] * sc[j];
   }
   for (int r = r_begin + rl; r < r_end; r += row_lanes) {
     const long long row = static_cast<long long>(b) * HW + r;
@@ -140,20 +151,20 @@ gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* stats, const 
   }
 }
 
+// stats_ws: max(B, 296) * 64 doubles of scratch (per-(sample, chunk, group) partial sums)
 int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma, const void* beta,
                    float eps, int silu, void* stats_ws, void* out, cudaStream_t stream) {
   const int C = C0 + C1;
   VTON_CHECK_ARG(B > 0 && HW > 0 && C > 0, "groupnorm: empty input");
   VTON_CHECK_ARG(C % GN_GROUPS == 0 && C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: C=%d must divide into 32 groups, sources multiple of 8", C);
   VTON_CHECK_ARG(C / 8 <= GN_THREADS, "groupnorm: C=%d too wide", C);
-  VTON_CHECK_ARG(stats_ws != nullptr, "groupnorm: stats workspace (B*32*2 doubles) required");
+  VTON_CHECK_ARG(stats_ws != nullptr, "groupnorm: stats workspace (max(B,296)*64 doubles) required");
   GnSrc src{static_cast<const __half*>(x0), static_cast<const __half*>(x1), C0, C1};
   int chunks = 296 / B;
   if (chunks < 1) chunks = 1;
   if (chunks > cdiv(HW, 16)) chunks = cdiv(HW, 16);
   const int rows_per_cta = cdiv(HW, chunks);
   chunks = cdiv(HW, rows_per_cta);
-  VTON_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * GN_GROUPS * B, stream));
   dim3 grid(chunks, B);
   gn_stats_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<double*>(stats_ws));
   gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<const double*>(stats_ws),

@@ -162,8 +162,8 @@ _gn_ws = {}
 def _stats_ws(device, B):
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _gn_ws.get(key)
-    if ws is None or ws.numel() < B * 64:
-        ws = torch.empty(max(B, 16) * 64, dtype=torch.float64, device=device)
+    if ws is None or ws.numel() < max(B, 296) * 64:
+        ws = torch.empty(max(B, 296) * 64, dtype=torch.float64, device=device)
         _gn_ws[key] = ws
     return ws
 

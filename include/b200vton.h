@@ -64,7 +64,8 @@ int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v
                        int B1, int kv1_off, float scale, int accumulate, void* stream);
 
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
- * fp32 statistics, optional SiLU, fp16 out [B*HW, C0+C1]. stats_ws: B*64 doubles of scratch.
+ * fp32 statistics (deterministic two-stage reduction, no atomics), optional SiLU, fp16 out [B*HW, C0+C1].
+ * stats_ws: max(B,296)*64 doubles of scratch.
  * diffusers ResnetBlock2D.norm1/norm2 (+nonlinearity), Transformer2DModel.norm
  * (src/transformerhacked_tryon.py:329), conv_norm_out + conv_act (src/unet_hacked_tryon.py:1384-1385). */
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,
