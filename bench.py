@@ -325,6 +325,16 @@ def run_b200(args, rank, world, local):
     n0 = L.launch_count()
     den.capture()
     launches_per_denoise_step = (L.launch_count() - n0) // 2     # capture() = one eager warm-up + one recorded pass
+    if args.profile_one_step:
+        # for `ncu --profile-from-start off`: exactly one denoise step (graph replay) inside the profiler range
+        den.step(0, torch.zeros_like(den.latents), use_graph=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        den.step(1, torch.zeros_like(den.latents), use_graph=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        log("profiled one denoise step; not a bench run")
+        return
     for _ in range(args.warmup):
         out = run_loop()
     torch.cuda.synchronize()
@@ -452,6 +462,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2, help="try-on requests per GPU per loop (BASELINE config 2: 2)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true", help="run one denoise step inside a cudaProfiler range (ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))

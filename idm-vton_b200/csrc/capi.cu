@@ -27,6 +27,7 @@ int timestep_embed_impl(const void* values, int n, int dim, int rows_repeat, voi
 int skinny_linear_impl(const void* x, int ldx, int M, int K, const void* W, long long ldw, int N, const void* bias,
                        int in_silu, int out_silu, const void* addend, int ld_add, void* out, int ldo,
                        cudaStream_t stream);
+void set_auto_v2(int on);
 int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const void* latents, const void* noise,
                   const void* coef, int do_cfg, void* out, cudaStream_t stream);
 }  // namespace vton
@@ -38,6 +39,14 @@ extern "C" {
 int b200vton_version(void) { return 100; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
+int b200vton_set_option(const char* name, int value) {
+  if (name && strcmp(name, "gemm_2cta_auto") == 0) {
+    vton::set_auto_v2(value);
+    return 0;
+  }
+  vton::set_last_error("unknown option %s", name ? name : "(null)");
+  return vton::kErrInvalid;
+}
 
 int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N,
                       int K, const void* bias, const void* residual, int64_t ldr, const void* rowvec,

@@ -10,39 +10,10 @@
 // tensor map over [B,H,W,C]; out-of-bounds box elements are zero-filled by TMA, which is the conv's zero padding.
 // Epilogue rounding points replicate the reference's fp16-autocast path:
 //   v = fp16(acc + bias); v = fp16(v + temb[b,n]); s = fp16(acc_sc + bias_sc); v = fp16(s + v); v = fp16(v + res)
-#include "common.cuh"
+#include "gemm_common.cuh"
 #include "host.h"
 
 namespace vton {
-
-struct GemmParams {
-  __half* out;
-  int ld_out;
-  int M, N;  // output rows / accumulator columns (GEGLU: N = 2 * out columns)
-  const __half* bias;
-  const __half* bias_sc;
-  const __half* residual;
-  int ld_res;
-  const __half* rowvec;  // per-sample row vector added after the bias rounding (time embedding), [B, ld_rowvec]
-  int ld_rowvec;
-  int rows_per_sample;
-  int slabs_main;  // 64-wide K slabs accumulated into accumulator 0
-  int slabs_sc;    // slabs accumulated into accumulator 1 (1x1 shortcut), 0 = none
-  int sc_split;    // shortcut slabs taken from source 0 before switching to source 1
-  // conv geometry
-  int conv;
-  int H, W, B;
-  int bw, bh, bb;  // TMA box extent in x / y / batch (bw*bh*bb == 128)
-  int tiles_x, tiles_y;
-  int cin_slabs;  // Cin / 64
-  int cout;       // rows per tap in the packed weight
-  int n_tiles;
-  int act_gelu;  // v = fp16(gelu_erf(fp16(acc + bias))) before the later epilogue terms (Resampler FeedForward)
-};
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_BYTES = BM * BK * 2;  // 16 KB
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -167,133 +138,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue (4 warps, thread = accumulator row) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int r_local = quarter * 32 + lane;
-    long long out_row = -1;
-    int sample = 0;
-    if (p.conv) {
-      const int lx = r_local % p.bw;
-      const int ly = (r_local / p.bw) % p.bh;
-      const int lb = r_local / (p.bw * p.bh);
-      const int b = b0 + lb, y = y0 + ly, x = x0 + lx;
-      if (b < p.B && y < p.H && x < p.W) out_row = (static_cast<long long>(b) * p.H + y) * p.W + x;
-      sample = b;
-    } else {
-      const int m = m_tile * BM + r_local;
-      if (m < p.M) out_row = m;
-      sample = p.rows_per_sample > 0 ? m / p.rows_per_sample : 0;
-    }
+    long long out_row;
+    int sample;
+    map_row(p, m_tile, quarter * 32 + lane, &out_row, &sample);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
-    const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
-    const int out_N = GEGLU ? p.N / 2 : p.N;
-#pragma unroll 1
-    for (int c = 0; c < OUT_COLS / 32; ++c) {
-      uint32_t acc[32];
-      uint32_t acc2[32];
-      tmem_ld_32x32(t_row + c * 32, acc);
-      if (GEGLU) {
-        tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
-      } else if (p.slabs_sc) {
-        tmem_ld_32x32(t_row + BN + c * 32, acc2);
-      }
-      tmem_ld_wait();
-      if (out_row < 0) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
-        if (ncol >= out_N) continue;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-        if (GEGLU) {
-          const int bcol = n0 + c * 32 + g * 8;  // packed (interleaved) bias index of the value half
-          float gt[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(acc2[g * 8 + j]);
-          if (p.bias) {
-            const uint4 bh = *reinterpret_cast<const uint4*>(p.bias + bcol);
-            const uint4 bg = *reinterpret_cast<const uint4*>(p.bias + bcol + BN / 2);
-            const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w};
-            const uint32_t bgw[4] = {bg.x, bg.y, bg.z, bg.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(bhw[j]);
-              const float2 b = unpack_h2(bgw[j]);
-              v[2 * j] += a.x;
-              v[2 * j + 1] += a.y;
-              gt[2 * j] += b.x;
-              gt[2 * j + 1] += b.y;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float hv = round_h(v[j]);
-            const float gv = round_h(gt[j]);
-            v[j] = hv * round_h(gelu_erf_f(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
-          }
-        } else {
-          if (p.bias) {
-            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + ncol);
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(bw[j]);
-              v[2 * j] += a.x;
-              v[2 * j + 1] += a.y;
-            }
-          }
-          if (p.act_gelu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
-          }
-          if (p.rowvec) {
-            const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
-            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(tw[j]);
-              v[2 * j] = round_h(v[2 * j]) + a.x;
-              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
-            }
-          }
-          if (p.slabs_sc) {
-            float s[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
-            if (p.bias_sc) {
-              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias_sc + ncol);
-              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a = unpack_h2(bw[j]);
-                s[2 * j] += a.x;
-                s[2 * j + 1] += a.y;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
-          }
-          if (p.residual) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(rw[j]);
-              v[2 * j] = round_h(v[2 * j]) + a.x;
-              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
-            }
-          }
-        }
-        uint4 o;
-        o.x = pack_h2(v[0], v[1]);
-        o.y = pack_h2(v[2], v[3]);
-        o.z = pack_h2(v[4], v[5]);
-        o.w = pack_h2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(p.out + out_row * p.ld_out + ncol) = o;
-      }
-    }
+    epilogue_store<BN, GEGLU>(p, t_row, BN, n_tile, out_row, sample);
   }
 
   tc_fence_before();
@@ -322,6 +173,33 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;
+}
+
+int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
+                   cudaStream_t stream);
+
+// force_bn encoding: 0 = automatic kernel / tile choice; 64..256 = 1-CTA kernel (gemm.cu) with that tile width;
+// 1000 + {128,160,192,256} = 2-CTA persistent kernel (gemm2.cu) with that tile width.
+static int g_auto_v2 = 1;
+void set_auto_v2(int on) { g_auto_v2 = on; }
+
+static int pick_bn2(int N, bool geglu) {
+  if (geglu) return N % 256 == 0 ? 256 : 128;
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  return N > 192 ? 256 : (N > 160 ? 192 : (N > 128 ? 160 : 128));
+}
+
+// Returns the 2-CTA tile width to use, or 0 for the 1-CTA kernel.
+static int choose_v2(int m_tiles, int N, bool geglu, bool has_shortcut, int force_bn) {
+  if (has_shortcut) return 0;   // the shortcut accumulator does not fit next to two accumulator stages
+  if (force_bn >= 1000) return force_bn - 1000;
+  if (force_bn != 0 || !g_auto_v2) return 0;
+  if (m_tiles < 4 || N < 128) return 0;
+  if (geglu && N % 128 != 0) return 0;
+  return pick_bn2(N, geglu);
 }
 
 static int pick_bn(int N, int force_bn) {
@@ -362,7 +240,9 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   VTON_CHECK_ARG(K % 64 == 0, "gemm: K=%d must be a multiple of 64", K);
   VTON_CHECK_ARG(N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "gemm: N/lda/ldw/ldo must be multiples of 8");
   VTON_CHECK_ARG(!geglu || (N % 16 == 0 && !residual && !rowvec), "gemm: bad GEGLU configuration");
-  int bn = pick_bn(N, force_bn);
+  const int bn2 = choose_v2(cdiv(M, BM), N, geglu != 0, false, force_bn);
+  VTON_CHECK_ARG(bn2 == 0 || bn2 == 128 || bn2 == 160 || bn2 == 192 || bn2 == 256, "gemm: bad 2-CTA tile width %d", bn2);
+  int bn = bn2 ? bn2 : pick_bn(N, force_bn);
   if (geglu && bn != 128 && bn != 256) bn = 128;
   VTON_CHECK_ARG(!geglu || N % bn == 0, "gemm: GEGLU needs N %% BN == 0 (N=%d, BN=%d)", N, bn);
   CUtensorMap tmA, tmB;
@@ -375,7 +255,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn2 ? bn / 2 : bn)};   // 2-CTA: each CTA loads half the tile
     if (int e = encode_tmap_f16(&tmB, W, 2, dims, strides, box)) return e;
   }
   GemmParams p{};
@@ -391,6 +271,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   p.rows_per_sample = rows_per_sample;
   p.slabs_main = K / 64;
   p.act_gelu = (flags & 2) ? 1 : 0;
+  if (bn2) return gemm2_dispatch(bn, geglu != 0, tmA, tmB, p, cdiv(M, BM), stream);
   return dispatch(bn, geglu != 0, tmA, tmB, tmA, tmA, tmB, p, cdiv(M, BM), stream);
 }
 
@@ -424,15 +305,18 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
   VTON_CHECK_ARG(Cout % 8 == 0 && ldo % 8 == 0 && ldx % 8 == 0, "conv3x3: Cout/ldo/ldx must be multiples of 8");
   VTON_CHECK_ARG(C0 % 64 == 0 && C1 % 64 == 0, "conv3x3: shortcut source channels must be multiples of 64");
   VTON_CHECK_ARG(!(w_sc && residual), "conv3x3: shortcut conv and identity residual are exclusive");
-  const int bn = pick_bn(Cout, force_bn);
   int bw, bh, bb;
   pick_box(B, H, W, &bw, &bh, &bb);
+  const int m_tiles_est = (W / bw) * cdiv(H, bh) * cdiv(B, bb);
+  const int bn2 = choose_v2(m_tiles_est, Cout, false, w_sc != nullptr, force_bn);
+  VTON_CHECK_ARG(bn2 == 0 || bn2 == 128 || bn2 == 160 || bn2 == 192 || bn2 == 256, "conv3x3: bad 2-CTA tile width %d", bn2);
+  const int bn = bn2 ? bn2 : pick_bn(Cout, force_bn >= 1000 ? 0 : force_bn);
   CUtensorMap tmA, tmB, tmS0, tmS1, tmBs;
   if (int e = encode_nhwc(&tmA, x, B, H, W, Cin, static_cast<int>(ldx), bw, bh, bb)) return e;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(9) * Cout};
     uint64_t strides[1] = {static_cast<uint64_t>(Cin) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn2 ? bn / 2 : bn)};
     if (int e = encode_tmap_f16(&tmB, w, 2, dims, strides, box)) return e;
   }
   tmS0 = tmA;
@@ -476,6 +360,7 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
   p.cin_slabs = Cin / 64;
   p.cout = Cout;
   const int m_tiles = p.tiles_x * p.tiles_y * cdiv(B, bb);
+  if (bn2) return gemm2_dispatch(bn, false, tmA, tmB, p, m_tiles, stream);
   return dispatch(bn, false, tmA, tmB, tmS0, tmS1, tmBs, p, m_tiles, stream);
 }
 

@@ -1,0 +1,218 @@
+// 2-CTA persistent tcgen05 GEMM / implicit-GEMM conv (sm_100a): the high-throughput path for the large linears and
+// 3x3 convolutions of both UNets (same math, operands, epilogue and rounding points as gemm.cu).
+//
+// A cluster of two CTAs (one SM pair) owns a 256 x BN output tile: CTA r stages its own 128 rows of A and one half
+// (BN/2 rows) of the weight tile per K slab, and the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) that reads
+// both CTAs' shared memory, so every operand byte fetched from L2 feeds twice the math of the 1-CTA kernel.
+// The kernel is persistent (one cluster per SM pair, static round-robin over tiles) and the fp32 accumulators are
+// double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> fp16 -> global) overlaps
+// the main loop of tile i+1.
+//   warp 0: TMA producer (both CTAs)      warp 1: MMA issuer (leader CTA) + TMEM alloc (both)
+//   warps 2..5: epilogue (both CTAs, thread = accumulator row of the CTA's own 128-row half)
+// Barriers: full[s] lives in the leader (both CTAs' TMA bytes are credited to it), empty[s] / tmem_full[a] are
+// multicast-committed to both CTAs, tmem_empty[a] lives in the leader and collects one arrive per epilogue warp (8).
+#include "gemm_common.cuh"
+#include "host.h"
+
+namespace vton {
+
+template <int BN, int STAGES>
+struct Smem2 {
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+};
+
+template <int BN, int STAGES, bool GEGLU>
+__global__ void __launch_bounds__(192, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+             int m_pairs) {
+  using L = Smem2<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int total_tiles = m_pairs * p.n_tiles;
+  const int slabs = p.slabs_main;
+  constexpr uint32_t kTmemCols = 512;   // two accumulator stages of BN (<= 256) columns
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);   // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();   // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit / TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA loads its own halves) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+        const int n_tile = t % p.n_tiles;
+        const int m_tile = 2 * (t / p.n_tiles) + static_cast<int>(rank);
+        const int n0 = n_tile * BN + static_cast<int>(rank) * (BN / 2);
+        int b0 = 0, y0 = 0, x0 = 0;
+        if (p.conv) {
+          x0 = (m_tile % p.tiles_x) * p.bw;
+          y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+          b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.bb;
+        }
+        for (int s = 0; s < slabs; ++s, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);   // both CTAs' bytes
+          if (p.conv) {
+            const int tap = s / p.cin_slabs;
+            const int c0 = (s - tap * p.cin_slabs) * BK;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma2_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 + dx, y0 + dy, b0);
+            tma2_load_2d(b_dst, &tmB, full_bar(stage), c0, tap * p.cout + n0);
+          } else {
+            tma2_load_2d(a_dst, &tmA, full_bar(stage), s * BK, m_tile * BM);
+            tma2_load_2d(b_dst, &tmB, full_bar(stage), s * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN, 0);
+      uint32_t it = 0;
+      int tile_iter = 0;
+      for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
+        const int acc = tile_iter & 1;
+        const uint32_t acc_phase = (tile_iter >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // both CTAs' epilogues drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int s = 0; s < slabs; ++s, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_src + k * 32, 0, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(b_src + k * 32, 0, 1024);
+            tc_mma_f16_2cta(d, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit_2cta(empty_bar(stage), 0x3);   // frees this smem slot in both CTAs
+        }
+        tc_commit_2cta(tfull_bar(acc), 0x3);        // accumulator stage complete, wake both epilogues
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs) =====================
+    const int quarter = warp & 3;
+    int tile_iter = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
+      const int acc = tile_iter & 1;
+      const uint32_t acc_phase = (tile_iter >> 1) & 1;
+      const int n_tile = t % p.n_tiles;
+      const int m_tile = 2 * (t / p.n_tiles) + static_cast<int>(rank);
+      long long out_row;
+      int sample;
+      map_row(p, m_tile, quarter * 32 + lane, &out_row, &sample);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      epilogue_store<BN, GEGLU>(p, t_row, 0, n_tile, out_row, sample);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);   // leader's barrier, one arrive per warp
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer may still be reading our smem / signalling our barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool GEGLU>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_pairs,
+                   cudaStream_t stream) {
+  using L = Smem2<BN, STAGES>;
+  auto kern = gemm2_kernel<BN, STAGES, GEGLU>;
+  static bool configured = false;
+  if (!configured) {
+    VTON_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = m_pairs * p.n_tiles;
+  const int clusters = tiles < kSMs / 2 ? tiles : kSMs / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VTON_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, m_pairs));
+  count_launch();
+  return kOk;
+}
+
+// bn in {128, 160, 192, 256}; weight-tile box = bn/2 rows
+int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
+                   cudaStream_t stream) {
+  p.n_tiles = cdiv(p.N, bn);
+  const int m_pairs = cdiv(m_tiles, 2);
+  if (geglu) {
+    if (bn == 256) return launch2<256, 6, true>(tmA, tmB, p, m_pairs, stream);
+    if (bn == 128) return launch2<128, 8, true>(tmA, tmB, p, m_pairs, stream);
+    set_last_error("gemm2: GEGLU epilogue supports BN 128/256 only (got %d)", bn);
+    return kErrUnsupported;
+  }
+  switch (bn) {
+    case 128: return launch2<128, 8, false>(tmA, tmB, p, m_pairs, stream);
+    case 160: return launch2<160, 7, false>(tmA, tmB, p, m_pairs, stream);
+    case 192: return launch2<192, 7, false>(tmA, tmB, p, m_pairs, stream);
+    case 256: return launch2<256, 6, false>(tmA, tmB, p, m_pairs, stream);
+  }
+  set_last_error("gemm2: unsupported BN %d", bn);
+  return kErrUnsupported;
+}
+
+}  // namespace vton

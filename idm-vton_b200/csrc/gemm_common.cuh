@@ -1,0 +1,174 @@
+// Shared pieces of the tcgen05 GEMM / implicit-conv kernels (gemm.cu: 1-CTA tiles, gemm2.cu: 2-CTA persistent):
+// the problem descriptor, the accumulator-row -> output-row mapping and the fused epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace vton {
+
+struct GemmParams {
+  __half* out;
+  int ld_out;
+  int M, N;  // output rows / accumulator columns (GEGLU: N = 2 * out columns)
+  const __half* bias;
+  const __half* bias_sc;
+  const __half* residual;
+  int ld_res;
+  const __half* rowvec;  // per-sample row vector added after the bias rounding (time embedding), [B, ld_rowvec]
+  int ld_rowvec;
+  int rows_per_sample;
+  int slabs_main;  // 64-wide K slabs accumulated into accumulator 0
+  int slabs_sc;    // slabs accumulated into accumulator 1 (1x1 shortcut), 0 = none
+  int sc_split;    // shortcut slabs taken from source 0 before switching to source 1
+  // conv geometry
+  int conv;
+  int H, W, B;
+  int bw, bh, bb;  // TMA box extent in x / y / batch (bw*bh*bb == 128)
+  int tiles_x, tiles_y;
+  int cin_slabs;  // Cin / 64
+  int cout;       // rows per tap in the packed weight
+  int n_tiles;
+  int act_gelu;  // v = fp16(gelu_erf(fp16(acc + bias))) before the later epilogue terms (Resampler FeedForward)
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+
+// Accumulator row r_local (0..127) of 128-row tile m_tile -> global output row (-1 = outside) and sample index.
+__device__ __forceinline__ void map_row(const GemmParams& p, int m_tile, int r_local, long long* out_row, int* sample) {
+  *out_row = -1;
+  if (p.conv) {
+    const int tx = m_tile % p.tiles_x;
+    const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+    const int tb = m_tile / (p.tiles_x * p.tiles_y);
+    const int lx = r_local % p.bw;
+    const int ly = (r_local / p.bw) % p.bh;
+    const int lb = r_local / (p.bw * p.bh);
+    const int b = tb * p.bb + lb, y = ty * p.bh + ly, x = tx * p.bw + lx;
+    if (b < p.B && y < p.H && x < p.W) *out_row = (static_cast<long long>(b) * p.H + y) * p.W + x;
+    *sample = b;
+  } else {
+    const int m = m_tile * BM + r_local;
+    if (m < p.M) *out_row = m;
+    *sample = p.rows_per_sample > 0 ? m / p.rows_per_sample : 0;
+  }
+}
+
+// TMEM -> registers -> fp16 -> global for one accumulator tile row. t_row: TMEM address (lane quarter | column base of
+// accumulator 0); the shortcut accumulator (if any) sits sc_col_off columns further. Warp-collective (tcgen05.ld).
+template <int BN, bool GEGLU>
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
+                                               long long out_row, int sample) {
+  const int n0 = n_tile * BN;
+    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+    const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
+    const int out_N = GEGLU ? p.N / 2 : p.N;
+#pragma unroll 1
+    for (int c = 0; c < OUT_COLS / 32; ++c) {
+      uint32_t acc[32];
+      uint32_t acc2[32];
+      tmem_ld_32x32(t_row + c * 32, acc);
+      if (GEGLU) {
+        tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
+      } else if (p.slabs_sc) {
+        tmem_ld_32x32(t_row + sc_col_off + c * 32, acc2);
+      }
+      tmem_ld_wait();
+      if (out_row < 0) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
+        if (ncol >= out_N) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+        if (GEGLU) {
+          const int bcol = n0 + c * 32 + g * 8;  // packed (interleaved) bias index of the value half
+          float gt[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(acc2[g * 8 + j]);
+          if (p.bias) {
+            const uint4 bh = *reinterpret_cast<const uint4*>(p.bias + bcol);
+            const uint4 bg = *reinterpret_cast<const uint4*>(p.bias + bcol + BN / 2);
+            const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w};
+            const uint32_t bgw[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(bhw[j]);
+              const float2 b = unpack_h2(bgw[j]);
+              v[2 * j] += a.x;
+              v[2 * j + 1] += a.y;
+              gt[2 * j] += b.x;
+              gt[2 * j + 1] += b.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float hv = round_h(v[j]);
+            const float gv = round_h(gt[j]);
+            v[j] = hv * round_h(gelu_erf_f(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
+          }
+        } else {
+          if (p.bias) {
+            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + ncol);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(bw[j]);
+              v[2 * j] += a.x;
+              v[2 * j + 1] += a.y;
+            }
+          }
+          if (p.act_gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
+          }
+          if (p.rowvec) {
+            const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
+            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(tw[j]);
+              v[2 * j] = round_h(v[2 * j]) + a.x;
+              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+            }
+          }
+          if (p.slabs_sc) {
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
+            if (p.bias_sc) {
+              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias_sc + ncol);
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 a = unpack_h2(bw[j]);
+                s[2 * j] += a.x;
+                s[2 * j + 1] += a.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
+          }
+          if (p.residual) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol);
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_h2(rw[j]);
+              v[2 * j] = round_h(v[2 * j]) + a.x;
+              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+            }
+          }
+        }
+        uint4 o;
+        o.x = pack_h2(v[0], v[1]);
+        o.y = pack_h2(v[2], v[3]);
+        o.z = pack_h2(v[4], v[5]);
+        o.w = pack_h2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.out + out_row * p.ld_out + ncol) = o;
+      }
+    }
+}
+
+}  // namespace vton

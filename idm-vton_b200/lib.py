@@ -53,12 +53,20 @@ def load(build_if_missing=True):
     lib.b200vton_version.restype = _i
     lib.b200vton_last_error.restype = _c.c_char_p
     lib.b200vton_launch_count.restype = _c.c_longlong
+    lib.b200vton_set_option.argtypes = [_c.c_char_p, _i]
+    lib.b200vton_set_option.restype = _i
+    if os.environ.get("B200VTON_GEMM2", "1") == "0":
+        lib.b200vton_set_option(b"gemm_2cta_auto", 0)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = _i
     _lib = lib
     return lib
+
+
+def set_option(name, value):
+    _check(load().b200vton_set_option(name.encode(), int(value)), "b200vton_set_option")
 
 
 def launch_count():

@@ -27,6 +27,9 @@ int b200vton_version(void);
 const char* b200vton_last_error(void);
 /* kernels launched (or recorded into a capturing stream) by this library since it was loaded */
 long long b200vton_launch_count(void);
+/* library options: "gemm_2cta_auto" = 1 (default) lets gemm / conv3x3 pick the 2-CTA persistent kernel for large
+ * problems when force_bn == 0; 0 keeps every launch on the 1-CTA kernel. */
+int b200vton_set_option(const char* name, int value);
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear on the hot path — attn to_q/to_k/to_v/to_out
  * (ip_adapter/attention_processor.py:240-268), Transformer2DModel.proj_in/proj_out
@@ -35,7 +38,8 @@ long long b200vton_launch_count(void);
  * flags & 1 (GEGLU): W/bias rows are tile-interleaved [value | gate] (see engine.pack_geglu) and
  *             out[M, N/2] = fp16(value) * fp16(gelu_erf(fp16(gate))).
  * flags & 2 (GELU): v = fp16(gelu_erf(fp16(acc + bias))) before the rowvec / residual terms (ip_adapter/resampler.py:13-20).
- * K % 64 == 0; N, lda, ldw, ldo % 8 == 0. force_bn: 0 = auto tile width, else 64/128/160/256. */
+ * K % 64 == 0; N, lda, ldw, ldo % 8 == 0. force_bn: 0 = automatic kernel and tile width; 64/128/160/256 = 1-CTA
+ * kernel with that tile width; 1000 + {128,160,192,256} = 2-CTA persistent kernel (cta_group::2) with that width. */
 int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N,
                       int K, const void* bias, const void* residual, int64_t ldr, const void* rowvec,
                       int64_t ld_rowvec, int rows_per_sample, int flags, int force_bn, void* stream);
