@@ -10,6 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from idm_vton_b200 import lib as L  # noqa: E402
 from idm_vton_b200.engine import pack_conv3x3, pack_geglu  # noqa: E402
 
+V2 = os.environ.get("MB_V2", "1") == "1"
+ONLY = os.environ.get("MB_ONLY", "")
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -60,10 +62,19 @@ def main():
                 continue
             ms = timeit(lambda: L.gemm(a, w, force_bn=bn))
             rec("gemm", ms, flops=2.0 * M * N * K, shape=[M, N, K], tag=tag, bn=bn)
+        if V2:
+            for bn in (128, 160, 192, 256):
+                if N % bn:
+                    continue
+                ms = timeit(lambda: L.gemm(a, w, force_bn=1000 + bn))
+                rec("gemm2", ms, flops=2.0 * M * N * K, shape=[M, N, K], tag=tag, bn=bn)
         if "ff1" in tag:
             wp, bp = pack_geglu(w, rnd(N), 256)
             ms = timeit(lambda: L.gemm(a, wp, bias=bp, geglu=True, force_bn=256))
             rec("gemm_geglu", ms, flops=2.0 * M * N * K, shape=[M, N, K], tag=tag, bn=256)
+            if V2:
+                ms = timeit(lambda: L.gemm(a, wp, bias=bp, geglu=True, force_bn=1256))
+                rec("gemm2_geglu", ms, flops=2.0 * M * N * K, shape=[M, N, K], tag=tag, bn=256)
         ref = timeit(lambda: torch.matmul(a, w.t()))
         rec("cublas", ref, flops=2.0 * M * N * K, shape=[M, N, K], tag=tag)
     # ---- convs (NHWC, B=4)
@@ -76,10 +87,15 @@ def main():
         for bn in ((160,) if Cout == 320 else (128, 256)):
             ms = timeit(lambda: L.conv3x3(x, w, bias=b, force_bn=bn))
             rec("conv3x3", ms, flops=2.0 * B * H * W * 9 * Cin * Cout, shape=[B, H, W, Cin, Cout], tag=tag, bn=bn)
+            if V2:
+                ms = timeit(lambda: L.conv3x3(x, w, bias=b, force_bn=1000 + bn))
+                rec("conv3x3_2cta", ms, flops=2.0 * B * H * W * 9 * Cin * Cout, shape=[B, H, W, Cin, Cout], tag=tag, bn=bn)
         xc = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
         wc = rnd(Cout, Cin, 3, 3).contiguous(memory_format=torch.channels_last)
         ref = timeit(lambda: torch.nn.functional.conv2d(xc, wc, b, padding=1))
         rec("cudnn", ref, flops=2.0 * B * H * W * 9 * Cin * Cout, shape=[B, H, W, Cin, Cout], tag=tag)
+    if ONLY == "gemm":
+        return
     # ---- attention
     for (B, H, N, Ng, tag) in [(4, 10, 3072, 3072, "L1 self+garment"), (4, 20, 768, 768, "L2 self+garment"),
                                (2, 10, 3072, 0, "L1 garment-unet self"), (4, 10, 3072, -77, "L1 cross text"),
