@@ -342,3 +342,39 @@ def test_gemm_auto_matches_1cta(lib):
     o_auto = lib.gemm(a, w)
     o_v1 = lib.gemm(a, w, force_bn=256)
     assert (o_auto.float() - o_v1.float()).abs().max() <= 2e-3 * o_v1.float().abs().max()
+
+
+# ------------------------------------------------------------------------------------------------
+# ping-pong attention kernel (attn2.cu, Nq >= 256) — the earlier attention tests with Nq >= 256 also run on it
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,Nq,N0,Ng", [(1, 1, 256, 128, 0), (2, 5, 3072, 3072, 3072), (2, 3, 300, 500, 77),
+                                          (2, 20, 768, 768, 768), (1, 2, 1024, 77, 0), (1, 2, 257, 16, 0)])
+def test_attention_pingpong(lib, B, H, Nq, N0, Ng):
+    C = H * 64
+    q, k, v = rnd(B, Nq, C, seed=1), rnd(B, N0, C, seed=2), rnd(B, N0, C, seed=3)
+    if Ng:
+        gk, gv = rnd(B, Ng, C, seed=4), rnd(B, Ng, C, seed=5)
+        out = lib.attention(q, k, v, gk, gv, kv1_off=0, heads=H)
+        ref = _attn_ref(q, torch.cat([k, gk], 1), torch.cat([v, gv], 1), H, 0.125)
+    else:
+        out = lib.attention(q, k, v, heads=H)
+        ref = _attn_ref(q, k, v, H, 0.125)
+    close(out, ref, tol=3e-3)
+
+
+def test_attention_pingpong_lazy_rescale(lib):
+    """Row maxima that grow by far more than 2^8 between K/V tiles force the TMEM rescale path."""
+    B, H, N = 1, 2, 512
+    C = H * 64
+    q = rnd(B, N, C, scale=3.0, seed=1)
+    k = rnd(B, N, C, scale=1.0, seed=2)
+    k[:, 256:] *= 6.0            # later tiles have much larger scores
+    v = rnd(B, N, C, seed=3)
+    out = lib.attention(q, k, v, heads=H)
+    close(out, _attn_ref(q, k, v, H, 0.125), tol=4e-3)
+    lib.set_option("attention_pingpong", 0)
+    try:
+        out1 = lib.attention(q, k, v, heads=H)
+    finally:
+        lib.set_option("attention_pingpong", 1)
+    close(out, out1, tol=4e-3)
