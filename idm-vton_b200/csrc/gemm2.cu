@@ -20,14 +20,16 @@ template <int BN, int STAGES>
 struct Smem2 {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;   // 2 staging buffers of 128 rows x 32 fp16 (64B-swizzled)
+  static constexpr int STORE_BYTES = 128 * 64;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + 2 * STORE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
 template <int BN, int STAGES, bool GEGLU>
 __global__ void __launch_bounds__(192, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
-             int m_pairs) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const GemmParams p, int m_pairs) {
   using L = Smem2<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -52,6 +54,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -134,7 +137,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue (both CTAs) =====================
+    // TMEM -> registers -> fused epilogue -> 64B-swizzled smem staging (32 columns at a time, double-buffered)
+    // -> TMA store: output rows leave the SM as full lines, asynchronously, and out-of-range rows / columns are
+    // clipped by the tensor map instead of by per-thread predicates.
     const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool store_thread = (threadIdx.x == 64);
+    uint8_t* stage_gen = smem_raw + (smem_base + L::STORE_OFFSET - smem_u32(smem_raw));
+    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+    uint32_t chunk_iter = 0;
     int tile_iter = 0;
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
       const int acc = tile_iter & 1;
@@ -143,15 +154,45 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int m_tile = 2 * (t / p.n_tiles) + static_cast<int>(rank);
       long long out_row;
       int sample;
-      map_row(p, m_tile, quarter * 32 + lane, &out_row, &sample);
+      map_row(p, m_tile, row, &out_row, &sample);
+      int b0 = 0, y0 = 0, x0 = 0;
+      if (p.conv) {
+        x0 = (m_tile % p.tiles_x) * p.bw;
+        y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+        b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.bb;
+      }
+      const int out_n0 = n_tile * OUT_COLS;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      epilogue_store<BN, GEGLU>(p, t_row, 0, n_tile, out_row, sample);
+#pragma unroll 1
+      for (int c = 0; c < OUT_COLS / 32; ++c, ++chunk_iter) {
+        const int buf = chunk_iter & 1;
+        uint32_t pk[16];
+        epilogue_chunk<BN, GEGLU>(p, t_row, 0, n_tile, out_row, sample, c, pk);
+        if (store_thread) tma_store_wait_read<1>();      // the store that last read this buffer has drained it
+        named_bar_sync(1, 128);
+        uint8_t* dst = stage_gen + buf * L::STORE_BYTES + row * 64;
+        const int sw = (row >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_thread) {
+          const uint32_t src = smem_base + L::STORE_OFFSET + buf * L::STORE_BYTES;
+          if (p.conv)
+            tma_store_4d(&tmOut, src, out_n0 + c * 32, x0, y0, b0);
+          else
+            tma_store_2d(&tmOut, src, out_n0 + c * 32, m_tile * BM);
+          tma_store_commit();
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);   // leader's barrier, one arrive per warp
     }
+    if (store_thread) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -166,8 +207,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool GEGLU>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_pairs,
-                   cudaStream_t stream) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmParams& p,
+                   int m_pairs, cudaStream_t stream) {
   using L = Smem2<BN, STAGES>;
   auto kern = gemm2_kernel<BN, STAGES, GEGLU>;
   static bool configured = false;
@@ -189,7 +230,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPar
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VTON_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, m_pairs));
+  VTON_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p, m_pairs));
   count_launch();
   return kOk;
 }
@@ -199,17 +240,33 @@ int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap
                    cudaStream_t stream) {
   p.n_tiles = cdiv(p.N, bn);
   const int m_pairs = cdiv(m_tiles, 2);
+  // output tensor map: [rows, out columns] (linear) or [B,H,W,out columns] (conv), 32-column boxes, 64B swizzle
+  CUtensorMap tmOut;
+  const int out_cols = geglu ? p.N / 2 : p.N;
+  if (p.conv) {
+    uint64_t dims[4] = {static_cast<uint64_t>(out_cols), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
+                        static_cast<uint64_t>(p.B)};
+    uint64_t strides[3] = {static_cast<uint64_t>(p.ld_out) * 2, static_cast<uint64_t>(p.W) * p.ld_out * 2,
+                           static_cast<uint64_t>(p.H) * p.W * p.ld_out * 2};
+    uint32_t box[4] = {32, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bb)};
+    if (int e = encode_tmap_f16(&tmOut, p.out, 4, dims, strides, box, nullptr, 64)) return e;
+  } else {
+    uint64_t dims[2] = {static_cast<uint64_t>(out_cols), static_cast<uint64_t>(p.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(p.ld_out) * 2};
+    uint32_t box[2] = {32, 128};
+    if (int e = encode_tmap_f16(&tmOut, p.out, 2, dims, strides, box, nullptr, 64)) return e;
+  }
   if (geglu) {
-    if (bn == 256) return launch2<256, 6, true>(tmA, tmB, p, m_pairs, stream);
-    if (bn == 128) return launch2<128, 8, true>(tmA, tmB, p, m_pairs, stream);
+    if (bn == 256) return launch2<256, 6, true>(tmA, tmB, tmOut, p, m_pairs, stream);
+    if (bn == 128) return launch2<128, 8, true>(tmA, tmB, tmOut, p, m_pairs, stream);
     set_last_error("gemm2: GEGLU epilogue supports BN 128/256 only (got %d)", bn);
     return kErrUnsupported;
   }
   switch (bn) {
-    case 128: return launch2<128, 8, false>(tmA, tmB, p, m_pairs, stream);
-    case 160: return launch2<160, 7, false>(tmA, tmB, p, m_pairs, stream);
-    case 192: return launch2<192, 7, false>(tmA, tmB, p, m_pairs, stream);
-    case 256: return launch2<256, 6, false>(tmA, tmB, p, m_pairs, stream);
+    case 128: return launch2<128, 8, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 160: return launch2<160, 7, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 192: return launch2<192, 7, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 256: return launch2<256, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
   }
   set_last_error("gemm2: unsupported BN %d", bn);
   return kErrUnsupported;

@@ -54,121 +54,161 @@ __device__ __forceinline__ void map_row(const GemmParams& p, int m_tile, int r_l
   }
 }
 
-// TMEM -> registers -> fp16 -> global for one accumulator tile row. t_row: TMEM address (lane quarter | column base of
-// accumulator 0); the shortcut accumulator (if any) sits sc_col_off columns further. Warp-collective (tcgen05.ld).
+// One 32-column chunk of the fused epilogue for one accumulator row: TMEM -> registers -> (bias, activation, temb,
+// shortcut, residual with the reference's fp16 rounding points) -> 16 packed half2 words. Warp-collective
+// (tcgen05.ld). t_row: TMEM address (lane quarter | column base of accumulator 0); the shortcut accumulator (if any)
+// sits sc_col_off columns further. Columns >= N of the last tile carry don't-care values (the sinks clip them).
+template <int BN, bool GEGLU>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
+                                               long long out_row, int sample, int c, uint32_t (&pk)[16]) {
+  const int n0 = n_tile * BN;
+  const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
+  const int out_N = GEGLU ? p.N / 2 : p.N;
+  uint32_t acc[32];
+  uint32_t acc2[32];
+  tmem_ld_32x32(t_row + c * 32, acc);
+  if (GEGLU) {
+    tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
+  } else if (p.slabs_sc) {
+    tmem_ld_32x32(t_row + sc_col_off + c * 32, acc2);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
+    const bool col_ok = ncol < out_N;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+    if (GEGLU) {
+      const int bcol = n0 + c * 32 + g * 8;  // packed (interleaved) bias index of the value half
+      float gt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(acc2[g * 8 + j]);
+      if (p.bias && col_ok) {
+        const uint4 bh = *reinterpret_cast<const uint4*>(p.bias + bcol);
+        const uint4 bg = *reinterpret_cast<const uint4*>(p.bias + bcol + BN / 2);
+        const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w};
+        const uint32_t bgw[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_h2(bhw[j]);
+          const float2 b = unpack_h2(bgw[j]);
+          v[2 * j] += a.x;
+          v[2 * j + 1] += a.y;
+          gt[2 * j] += b.x;
+          gt[2 * j + 1] += b.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float hv = round_h(v[j]);
+        const float gv = round_h(gt[j]);
+        v[j] = hv * round_h(gelu_erf_f(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
+      }
+    } else {
+      if (p.bias && col_ok) {
+        const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + ncol);
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_h2(bw[j]);
+          v[2 * j] += a.x;
+          v[2 * j + 1] += a.y;
+        }
+      }
+      if (p.act_gelu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
+      }
+      if (p.rowvec && col_ok) {
+        const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
+        const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_h2(tw[j]);
+          v[2 * j] = round_h(v[2 * j]) + a.x;
+          v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+        }
+      }
+      if (p.slabs_sc) {
+        float s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
+        if (p.bias_sc && col_ok) {
+          const uint4 bv = *reinterpret_cast<const uint4*>(p.bias_sc + ncol);
+          const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = unpack_h2(bw[j]);
+            s[2 * j] += a.x;
+            s[2 * j + 1] += a.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
+      }
+      if (p.residual && col_ok && out_row >= 0) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol);
+        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_h2(rw[j]);
+          v[2 * j] = round_h(v[2 * j]) + a.x;
+          v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+        }
+      }
+    }
+    pk[g * 4 + 0] = pack_h2(v[0], v[1]);
+    pk[g * 4 + 1] = pack_h2(v[2], v[3]);
+    pk[g * 4 + 2] = pack_h2(v[4], v[5]);
+    pk[g * 4 + 3] = pack_h2(v[6], v[7]);
+  }
+}
+
+// Sink 1 (1-CTA kernel): registers -> global, each thread writes its own row.
 template <int BN, bool GEGLU>
 __device__ __forceinline__ void epilogue_store(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
                                                long long out_row, int sample) {
-  const int n0 = n_tile * BN;
-    constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
-    const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
-    const int out_N = GEGLU ? p.N / 2 : p.N;
+  constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
+  const int out_n0 = GEGLU ? n_tile * (BN / 2) : n_tile * BN;
+  const int out_N = GEGLU ? p.N / 2 : p.N;
 #pragma unroll 1
-    for (int c = 0; c < OUT_COLS / 32; ++c) {
-      uint32_t acc[32];
-      uint32_t acc2[32];
-      tmem_ld_32x32(t_row + c * 32, acc);
-      if (GEGLU) {
-        tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
-      } else if (p.slabs_sc) {
-        tmem_ld_32x32(t_row + sc_col_off + c * 32, acc2);
-      }
-      tmem_ld_wait();
-      if (out_row < 0) continue;
+  for (int c = 0; c < OUT_COLS / 32; ++c) {
+    uint32_t pk[16];
+    epilogue_chunk<BN, GEGLU>(p, t_row, sc_col_off, n_tile, out_row, sample, c, pk);
+    if (out_row < 0) continue;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
-        if (ncol >= out_N) continue;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-        if (GEGLU) {
-          const int bcol = n0 + c * 32 + g * 8;  // packed (interleaved) bias index of the value half
-          float gt[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(acc2[g * 8 + j]);
-          if (p.bias) {
-            const uint4 bh = *reinterpret_cast<const uint4*>(p.bias + bcol);
-            const uint4 bg = *reinterpret_cast<const uint4*>(p.bias + bcol + BN / 2);
-            const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w};
-            const uint32_t bgw[4] = {bg.x, bg.y, bg.z, bg.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(bhw[j]);
-              const float2 b = unpack_h2(bgw[j]);
-              v[2 * j] += a.x;
-              v[2 * j + 1] += a.y;
-              gt[2 * j] += b.x;
-              gt[2 * j + 1] += b.y;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float hv = round_h(v[j]);
-            const float gv = round_h(gt[j]);
-            v[j] = hv * round_h(gelu_erf_f(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
-          }
-        } else {
-          if (p.bias) {
-            const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + ncol);
-            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(bw[j]);
-              v[2 * j] += a.x;
-              v[2 * j + 1] += a.y;
-            }
-          }
-          if (p.act_gelu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
-          }
-          if (p.rowvec) {
-            const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
-            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(tw[j]);
-              v[2 * j] = round_h(v[2 * j]) + a.x;
-              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
-            }
-          }
-          if (p.slabs_sc) {
-            float s[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
-            if (p.bias_sc) {
-              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias_sc + ncol);
-              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a = unpack_h2(bw[j]);
-                s[2 * j] += a.x;
-                s[2 * j + 1] += a.y;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
-          }
-          if (p.residual) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_h2(rw[j]);
-              v[2 * j] = round_h(v[2 * j]) + a.x;
-              v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
-            }
-          }
-        }
-        uint4 o;
-        o.x = pack_h2(v[0], v[1]);
-        o.y = pack_h2(v[2], v[3]);
-        o.z = pack_h2(v[4], v[5]);
-        o.w = pack_h2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(p.out + out_row * p.ld_out + ncol) = o;
-      }
+    for (int g = 0; g < 4; ++g) {
+      const int ncol = out_n0 + c * 32 + g * 8;
+      if (ncol >= out_N) continue;
+      *reinterpret_cast<uint4*>(p.out + out_row * p.ld_out + ncol) =
+          make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
     }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA stores (smem -> global, bulk async group); out-of-bounds box elements are clipped by the hardware.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 }  // namespace vton

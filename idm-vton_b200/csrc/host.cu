@@ -40,7 +40,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* elem_strides) {
+                    const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -67,7 +67,8 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
     }
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, gbox, gel, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstr, gbox, gel, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,

@@ -32,10 +32,11 @@ const char* get_last_error();
     }                                                                                            \
   } while (0)
 
-// Encodes a tiled fp16 tensor map with SWIZZLE_128B (inner box must be 64 halves = 128 B).
+// Encodes a tiled fp16 tensor map with SWIZZLE_128B (inner box = 64 halves = 128 B) or, with swizzle_bytes = 64,
+// SWIZZLE_64B (inner box = 32 halves).
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1. Returns 0 on success.
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* elem_strides = nullptr);
+                    const uint32_t* box, const uint32_t* elem_strides = nullptr, int swizzle_bytes = 128);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -299,7 +299,8 @@ class UNetEngine:
             L.attention(q2, kv_i[..., :C], kv_i[..., C:], heads=H, accumulate=True, out=a2)
         h = L.gemm(a2.view(B * N, C), blk.wo2, bias=blk.bo2, residual=h)
         n3 = L.layernorm(h, blk.ln3w, blk.ln3b)
-        ff = L.gemm(n3, blk.wff1, bias=blk.bff1, geglu=True, force_bn=blk.ff_bn)
+        ff = L.gemm(n3, blk.wff1, bias=blk.bff1, geglu=True,
+                    force_bn=(1000 + blk.ff_bn) if n3.shape[0] >= 512 else blk.ff_bn)   # 2-CTA kernel for large M
         return L.gemm(ff, blk.wff2, bias=blk.bff2, residual=h)
 
     def _t2d(self, t, x, state):
