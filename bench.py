@@ -315,6 +315,8 @@ def run_b200(args, rank, world, local):
     def run_loop():
         """One bench step: the full 30-step denoising loop for one batch (inputs resident in HBM)."""
         den.latents.copy_(req["latents"])
+        if den.hoist_garment:
+            den.precompute_garment()      # the 30 garment-UNet passes of this request (batched) + garment K/V
         for i in range(STEPS_DENOISE):
             noise = torch.randn(den.latents.shape, generator=gen, device=device, dtype=torch.float16)
             den.step(i, noise, use_graph=True)
@@ -349,12 +351,14 @@ def run_b200(args, rank, world, local):
     # ---- timed region (device events; max over ranks)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    eager0 = L.launch_count()
     with ClockSampler(local) as clocks:
         for s, e in evs:
             s.record()
             run_loop()
             e.record()
         barrier()
+    eager_launches = L.launch_count() - eager0      # launches outside the graph (hoisted garment passes)
     per_step_ms = [s.elapsed_time(e) for s, e in evs]
     total_ms = evs[0][0].elapsed_time(evs[-1][1])
     if world > 1:
@@ -436,7 +440,9 @@ def run_b200(args, rank, world, local):
                    "global_batch": world * B, "weights": "random SDXL-shaped (try-on 2.99B + garment 2.56B params, fp16)",
                    "inputs": "larger than L2 (11 GB of weights streamed every denoise step)",
                    "parallelism": f"independent requests x{world}, weights NCCL-broadcast at load",
-                   "cuda_graph": True},
+                   "cuda_graph": True,
+                   "garment_unet": "all 30 passes of a request hoisted before the loop and batched (inside the timed "
+                                   "region); try-on UNet per step from one CUDA graph"},
         "p50_latency_ms_per_image": statistics.median(per_step_ms),
         "latency_note": "latency of an image = loop time of the batch it belongs to",
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -445,8 +451,9 @@ def run_b200(args, rank, world, local):
                      "algorithmic_tflop_per_denoise_step": fl / STEPS_DENOISE / 1e12},
         "cpu_baseline": cpu,
         "e2e": e2e,
-        "gpu_launches": launches_per_denoise_step * STEPS_DENOISE * args.steps,
-        "launches_per_denoise_step": launches_per_denoise_step,
+        "gpu_launches": launches_per_denoise_step * STEPS_DENOISE * args.steps + eager_launches,
+        "launches_per_denoise_step_graph": launches_per_denoise_step,
+        "launches_hoisted_garment_per_loop": eager_launches // max(args.steps, 1),
         "clocks": clocks.summary(),
         "weights_broadcast_ms": bcast_ms,
     }

@@ -24,7 +24,8 @@ struct AttnParams {
   int ld_out;
   int B, H, Nq, N0, N1;
   int kv1_off;    // segment-1 sample index = (b - kv1_off) % kv1_count; negative => zero K/V closed form
-  int kv1_count;  // number of samples in the segment-1 tensors
+  int kv1_count;  // segment-1 sample index is taken modulo this count
+  const int* kv1_base;  // optional device scalar added to the segment-1 sample index (hoisted per-step K/V)
   float scale_log2;
   int accumulate;
 };
@@ -73,7 +74,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   int idx1 = -1;
   if (p.N1 > 0) {
     idx1 = b - p.kv1_off;
-    if (idx1 >= 0) idx1 %= p.kv1_count;
+    if (idx1 >= 0) idx1 = idx1 % p.kv1_count + (p.kv1_base ? *p.kv1_base : 0);
   }
   const bool zero_kv = (p.N1 > 0) && (idx1 < 0);
   const int tiles1 = (p.N1 > 0 && idx1 >= 0) ? ((p.N1 + 127) >> 7) : 0;
@@ -278,7 +279,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
 int attn2_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                  const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, float scale_log2, int accumulate, cudaStream_t stream);
+                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream);
 
 static int g_attn_v2 = 1;   // 1: use the ping-pong kernel (attn2.cu) for Nq >= 256
 void set_attn_v2(int on) { g_attn_v2 = on; }
@@ -293,7 +294,7 @@ static int encode_tokens(CUtensorMap* tm, const void* base, long long ld, int co
 // q: [B, Nq, >=H*64] (row stride ldq); k0/v0: [B, N0, .] (ldkv0); k1/v1: [B1, N1, .] (ldkv1); out: [B, Nq, .] (ldo)
 int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long long ldkv0, const void* k1,
               const void* v1, long long ldkv1, void* out, long long ldo, int B, int H, int Nq, int N0, int N1, int B1,
-              int kv1_off, float scale, int accumulate, cudaStream_t stream) {
+              int kv1_off, int kv1_mod, const void* kv1_base, float scale, int accumulate, cudaStream_t stream) {
   VTON_CHECK_ARG(B > 0 && H > 0 && Nq > 0 && N0 > 0 && N1 >= 0, "attn: bad sizes B=%d H=%d Nq=%d N0=%d N1=%d", B, H, Nq, N0, N1);
   VTON_CHECK_ARG(ldq % 8 == 0 && ldkv0 % 8 == 0 && ldo % 8 == 0, "attn: row strides must be multiples of 8");
   VTON_CHECK_ARG(B <= 65535 && H <= 65535, "attn: grid too large");
@@ -312,8 +313,8 @@ int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long
   }
   if (g_attn_v2 && Nq >= 256) {
     return attn2_launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
-                        has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? B1 : 1, scale * 1.4426950408889634f, accumulate,
-                        stream);
+                        has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,
+                        has1 ? static_cast<const int*>(kv1_base) : nullptr, scale * 1.4426950408889634f, accumulate, stream);
   }
   AttnParams p{};
   p.out = static_cast<__half*>(out);
@@ -324,7 +325,8 @@ int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long
   p.N0 = N0;
   p.N1 = N1;
   p.kv1_off = has1 ? kv1_off : (N1 > 0 ? B : 0);
-  p.kv1_count = has1 ? B1 : 1;
+  p.kv1_count = has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1;
+  p.kv1_base = has1 ? static_cast<const int*>(kv1_base) : nullptr;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
   static bool configured = false;

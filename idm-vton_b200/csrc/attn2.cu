@@ -21,6 +21,7 @@ struct Attn2Params {
   int ld_out;
   int B, H, Nq, N0, N1;
   int kv1_off, kv1_count;
+  const int* kv1_base;
   float scale_log2;
   int accumulate;
 };
@@ -67,7 +68,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   int idx1 = -1;
   if (p.N1 > 0) {
     idx1 = b - p.kv1_off;
-    if (idx1 >= 0) idx1 %= p.kv1_count;
+    if (idx1 >= 0) idx1 = idx1 % p.kv1_count + (p.kv1_base ? *p.kv1_base : 0);
   }
   const bool zero_kv = (p.N1 > 0) && (idx1 < 0);
   const int tiles1 = (p.N1 > 0 && idx1 >= 0) ? ((p.N1 + 127) >> 7) : 0;
@@ -323,7 +324,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
 int attn2_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                  const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, float scale_log2, int accumulate, cudaStream_t stream) {
+                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream) {
   Attn2Params p{};
   p.out = out;
   p.ld_out = ld_out;
@@ -334,6 +335,7 @@ int attn2_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensor
   p.N1 = N1;
   p.kv1_off = kv1_off;
   p.kv1_count = kv1_count;
+  p.kv1_base = kv1_base;
   p.scale_log2 = scale_log2;
   p.accumulate = accumulate;
   static bool configured = false;

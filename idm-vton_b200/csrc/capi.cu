@@ -13,7 +13,7 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
                  cudaStream_t stream);
 int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long long ldkv0, const void* k1,
               const void* v1, long long ldkv1, void* out, long long ldo, int B, int H, int Nq, int N0, int N1, int B1,
-              int kv1_off, float scale, int accumulate, cudaStream_t stream);
+              int kv1_off, int kv1_mod, const void* kv1_base, float scale, int accumulate, cudaStream_t stream);
 int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma, const void* beta,
                    float eps, int silu, void* stats_ws, void* out, cudaStream_t stream);
 int layernorm_impl(const void* x, long long ldx, int rows, int C, const void* gamma, const void* beta, float eps,
@@ -70,8 +70,9 @@ int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int C
 
 int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v0, int64_t ldkv0, const void* k1,
                        const void* v1, int64_t ldkv1, void* out, int64_t ldo, int B, int H, int Nq, int N0, int N1,
-                       int B1, int kv1_off, float scale, int accumulate, void* stream) {
-  return vton::attn_impl(q, ldq, k0, v0, ldkv0, k1, v1, ldkv1, out, ldo, B, H, Nq, N0, N1, B1, kv1_off, scale,
+                       int B1, int kv1_off, int kv1_mod, const void* kv1_base, float scale, int accumulate,
+                       void* stream) {
+  return vton::attn_impl(q, ldq, k0, v0, ldkv0, k1, v1, ldkv1, out, ldo, B, H, Nq, N0, N1, B1, kv1_off, kv1_mod, kv1_base, scale,
                          accumulate, S(stream));
 }
 

@@ -5,8 +5,8 @@
 // (BN/2 rows) of the weight tile per K slab, and the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) that reads
 // both CTAs' shared memory, so every operand byte fetched from L2 feeds twice the math of the 1-CTA kernel.
 // The kernel is persistent (one cluster per SM pair, static round-robin over tiles) and the fp32 accumulators are
-// double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> fp16 -> global) overlaps
-// the main loop of tile i+1.
+// double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> fp16 -> swizzled smem ->
+// per-warp TMA stores) overlaps the main loop of tile i+1.
 //   warp 0: TMA producer (both CTAs)      warp 1: MMA issuer (leader CTA) + TMEM alloc (both)
 //   warps 2..5: epilogue (both CTAs, thread = accumulator row of the CTA's own 128-row half)
 // Barriers: full[s] lives in the leader (both CTAs' TMA bytes are credited to it), empty[s] / tmem_full[a] are
@@ -20,9 +20,10 @@ template <int BN, int STAGES>
 struct Smem2 {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;   // 2 staging buffers of 128 rows x 32 fp16 (64B-swizzled)
-  static constexpr int STORE_BYTES = 128 * 64;
-  static constexpr int BAR_OFFSET = STORE_OFFSET + 2 * STORE_BYTES;
+  // epilogue staging: per warp one 32-row x 32-column fp16 buffer (2 KB, 64B-swizzled) per chunk of the tile
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STORE_BYTES = 4 * (BN / 32) * 2048;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + STORE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
@@ -137,15 +138,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue (both CTAs) =====================
-    // TMEM -> registers -> fused epilogue -> 64B-swizzled smem staging (32 columns at a time, double-buffered)
-    // -> TMA store: output rows leave the SM as full lines, asynchronously, and out-of-range rows / columns are
-    // clipped by the tensor map instead of by per-thread predicates.
+    // TMEM -> registers -> fused epilogue -> 64B-swizzled smem staging -> TMA store. Every warp owns a private ring of
+    // staging buffers (one 32-row x 32-column buffer per chunk of the tile) and issues its own bulk stores, so the
+    // epilogue needs no CTA-wide barrier and never waits for a store inside a tile: the buffers are only recycled at
+    // the next tile, a full main loop later. Rows / columns outside the output are clipped by the tensor map.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const bool store_thread = (threadIdx.x == 64);
-    uint8_t* stage_gen = smem_raw + (smem_base + L::STORE_OFFSET - smem_u32(smem_raw));
     constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
-    uint32_t chunk_iter = 0;
+    constexpr int NCHUNK = OUT_COLS / 32;
+    const uint32_t my_stage = smem_base + L::STORE_OFFSET + quarter * (NCHUNK * 2048);
+    uint8_t* my_stage_gen = smem_raw + (my_stage - smem_u32(smem_raw));
+    const int sw = (lane >> 1) & 3;
+    // origin of this warp's 32 accumulator rows inside the conv tile box (rows are ordered x fastest, then y, then b)
+    const int qx = p.conv ? (quarter * 32) % p.bw : 0;
+    const int qy = p.conv ? ((quarter * 32) / p.bw) % p.bh : 0;
+    const int qb = p.conv ? (quarter * 32) / (p.bw * p.bh) : 0;
     int tile_iter = 0;
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
       const int acc = tile_iter & 1;
@@ -162,29 +169,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.bb;
       }
       const int out_n0 = n_tile * OUT_COLS;
+      if (lane == 0) tma_store_wait_read<0>();   // this warp's stores of the previous tile have drained the ring
+      __syncwarp();
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < OUT_COLS / 32; ++c, ++chunk_iter) {
-        const int buf = chunk_iter & 1;
+      for (int c = 0; c < NCHUNK; ++c) {
         uint32_t pk[16];
         epilogue_chunk<BN, GEGLU>(p, t_row, 0, n_tile, out_row, sample, c, pk);
-        if (store_thread) tma_store_wait_read<1>();      // the store that last read this buffer has drained it
-        named_bar_sync(1, 128);
-        uint8_t* dst = stage_gen + buf * L::STORE_BYTES + row * 64;
-        const int sw = (row >> 1) & 3;
+        uint8_t* dst = my_stage_gen + c * 2048 + lane * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (store_thread) {
-          const uint32_t src = smem_base + L::STORE_OFFSET + buf * L::STORE_BYTES;
+        __syncwarp();
+        if (lane == 0) {
           if (p.conv)
-            tma_store_4d(&tmOut, src, out_n0 + c * 32, x0, y0, b0);
+            tma_store_4d(&tmOut, my_stage + c * 2048, out_n0 + c * 32, x0 + qx, y0 + qy, b0 + qb);
           else
-            tma_store_2d(&tmOut, src, out_n0 + c * 32, m_tile * BM);
+            tma_store_2d(&tmOut, my_stage + c * 2048, out_n0 + c * 32, m_tile * BM + quarter * 32);
           tma_store_commit();
         }
       }
@@ -192,7 +196,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);   // leader's barrier, one arrive per warp
     }
-    if (store_thread) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -248,25 +252,29 @@ int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap
                         static_cast<uint64_t>(p.B)};
     uint64_t strides[3] = {static_cast<uint64_t>(p.ld_out) * 2, static_cast<uint64_t>(p.W) * p.ld_out * 2,
                            static_cast<uint64_t>(p.H) * p.W * p.ld_out * 2};
-    uint32_t box[4] = {32, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bb)};
+    // a warp stores 32 consecutive tile rows = a rectangular sub-box of the (bw, bh, bb) pixel box
+    const uint32_t sbw = p.bw < 32 ? p.bw : 32;
+    const uint32_t sbh = static_cast<uint32_t>(p.bh) < 32 / sbw ? p.bh : 32 / sbw;
+    const uint32_t sbb = 32 / (sbw * sbh);
+    uint32_t box[4] = {32, sbw, sbh, sbb};
     if (int e = encode_tmap_f16(&tmOut, p.out, 4, dims, strides, box, nullptr, 64)) return e;
   } else {
     uint64_t dims[2] = {static_cast<uint64_t>(out_cols), static_cast<uint64_t>(p.M)};
     uint64_t strides[1] = {static_cast<uint64_t>(p.ld_out) * 2};
-    uint32_t box[2] = {32, 128};
+    uint32_t box[2] = {32, 32};
     if (int e = encode_tmap_f16(&tmOut, p.out, 2, dims, strides, box, nullptr, 64)) return e;
   }
   if (geglu) {
-    if (bn == 256) return launch2<256, 6, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-    if (bn == 128) return launch2<128, 8, true>(tmA, tmB, tmOut, p, m_pairs, stream);
+    if (bn == 256) return launch2<256, 5, true>(tmA, tmB, tmOut, p, m_pairs, stream);
+    if (bn == 128) return launch2<128, 7, true>(tmA, tmB, tmOut, p, m_pairs, stream);
     set_last_error("gemm2: GEGLU epilogue supports BN 128/256 only (got %d)", bn);
     return kErrUnsupported;
   }
   switch (bn) {
-    case 128: return launch2<128, 8, false>(tmA, tmB, tmOut, p, m_pairs, stream);
-    case 160: return launch2<160, 7, false>(tmA, tmB, tmOut, p, m_pairs, stream);
-    case 192: return launch2<192, 7, false>(tmA, tmB, tmOut, p, m_pairs, stream);
-    case 256: return launch2<256, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 128: return launch2<128, 7, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 160: return launch2<160, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 192: return launch2<192, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+    case 256: return launch2<256, 5, false>(tmA, tmB, tmOut, p, m_pairs, stream);
   }
   set_last_error("gemm2: unsupported BN %d", bn);
   return kErrUnsupported;

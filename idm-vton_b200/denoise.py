@@ -13,12 +13,20 @@ from .engine import CIN_PAD, UNetEngine
 
 
 class TryOnDenoiser:
-    def __init__(self, tryon: UNetEngine, garment: UNetEngine):
+    def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=8):
+        """hoist_garment: the garment UNet depends on the timestep but not on the latents, so all
+        its passes are run BEFORE the loop, batched over `garment_chunk` timesteps at a time (large-M GEMMs, weights
+        read once per chunk instead of once per step), and the garment K/V of every try-on block are projected once
+        for all steps; the per-step graph then contains the try-on UNet only and walks the K/V by a device-side
+        step index. Exactly the same arithmetic per (step, garment) as the step-by-step order."""
         self.tryon = tryon
         self.garment = garment
         self.L = tryon.L
         self.device = tryon.device
         self._graph = None
+        self.hoist_garment = hoist_garment
+        self.garment_chunk = garment_chunk
+        self.gkv_all = None
 
     # -------------------------------------------------------------------------------------------
     def prepare(self, latents, mask, masked_image_latents, pose_latents, cloth_latents, prompt_embeds,
@@ -51,7 +59,9 @@ class TryOnDenoiser:
         self.aug = self.tryon.aug_embedding(add_text_embeds.to(dev, f16), add_time_ids.to(dev))
         self.t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.coef = torch.zeros(6, dtype=torch.float32, device=dev)
+        self.step_base = torch.zeros(1, dtype=torch.int32, device=dev)     # = step index * Bg (hoisted garment K/V)
         self.eps = None
+        self.gkv_all = None
 
     def set_step_tables(self, scheduler, timesteps):
         """Uploads the per-step scalars: t and {gs, sqrt(1-abar), 1/sqrt(abar), c0, c1, sigma}."""
@@ -60,19 +70,48 @@ class TryOnDenoiser:
             rows.append([self.guidance_scale, *scheduler.step_coefficients(int(t))])
         self.coef_table = torch.tensor(rows, dtype=torch.float32, device=self.device)
         self.t_table = torch.tensor([float(int(t)) for t in timesteps], dtype=torch.float32, device=self.device)
+        self.base_table = torch.arange(len(rows), dtype=torch.int32, device=self.device) * self.Bg
+        if self.hoist_garment:
+            self.precompute_garment()
+
+    def precompute_garment(self):
+        """All garment-UNet passes of the request (one per timestep), batched, then the garment K/V projection of every
+        try-on block for all timesteps: gkv_all[i] = [T*Bg, Ng, 2C] in timestep-major order."""
+        L = self.L
+        T, Bg = self.t_table.numel(), self.Bg
+        blocks = self.tryon.blocks()
+        self.gkv_all = None
+        gkv = None
+        for c0 in range(0, T, self.garment_chunk):
+            n = min(self.garment_chunk, T - c0)
+            t_rows = self.t_table[c0:c0 + n].repeat_interleave(Bg).contiguous()            # timestep-major rows
+            x_big = self.x_g.repeat(n, 1, 1, 1)
+            ctx_big = [(kv_t.repeat(n, 1, 1), None) for kv_t, _ in self.ctx_g]
+            feats = []
+            self.garment.forward(x_big, self.garment.time_embedding(t_rows, n * Bg), ctx_big, collect=feats)
+            if gkv is None:
+                gkv = [torch.empty((T * Bg, f.shape[1], 2 * f.shape[2]), dtype=torch.float16, device=self.device)
+                       for f in feats]
+            for i, (blk, f) in enumerate(zip(blocks, feats)):
+                self.tryon.garment_kv(blk, f, out=gkv[i][c0 * Bg:(c0 + n) * Bg])
+            del feats, x_big, ctx_big
+        self.gkv_all = gkv
 
     # -------------------------------------------------------------------------------------------
     def _launch_step(self):
         """The launch sequence of one denoise step over the static buffers (graph-capturable)."""
         L = self.L
         L.nchw_to_nhwc(self.latents, self.x_t, c_off=0)          # CFG duplication + channel concat as offsets
-        feats = []
-        temb_g = self.garment.time_embedding(self.t_dev, self.Bg)
-        self.garment.forward(self.x_g, temb_g, self.ctx_g, collect=feats)
         temb_t = self.tryon.time_embedding(self.t_dev, self.Bt, self.aug)
-        gf = feats
         n_persons = self.B if self.do_cfg else 0
-        self.eps = self.tryon.forward(self.x_t, temb_t, self.ctx_t, gfeats=gf, n_persons=n_persons)
+        if self.gkv_all is not None:
+            self.eps = self.tryon.forward(self.x_t, temb_t, self.ctx_t, n_persons=n_persons,
+                                          gkv_pre=(self.gkv_all, self.Bg, self.step_base))
+        else:
+            feats = []
+            temb_g = self.garment.time_embedding(self.t_dev, self.Bg)
+            self.garment.forward(self.x_g, temb_g, self.ctx_g, collect=feats)
+            self.eps = self.tryon.forward(self.x_t, temb_t, self.ctx_t, gfeats=feats, n_persons=n_persons)
         L.cfg_ddpm_step(self.eps, self.latents, self.noise, self.coef, do_cfg=self.do_cfg, out=self.latents_next)
         self.latents.copy_(self.latents_next)
 
@@ -95,6 +134,7 @@ class TryOnDenoiser:
         """Runs denoise step i (tables from set_step_tables). noise: [B,4,h,w] fp16 variance noise or None."""
         self.t_dev.copy_(self.t_table[i:i + 1])
         self.coef.copy_(self.coef_table[i])
+        self.step_base.copy_(self.base_table[i:i + 1])
         if noise is not None:
             self.noise.copy_(noise)
         else:
@@ -104,6 +144,7 @@ class TryOnDenoiser:
                 self.capture()
                 self.t_dev.copy_(self.t_table[i:i + 1])
                 self.coef.copy_(self.coef_table[i])
+                self.step_base.copy_(self.base_table[i:i + 1])
             self._graph.replay()
         else:
             self._launch_step()

@@ -252,12 +252,19 @@ class UNetEngine:
     # per-step pieces
     # -------------------------------------------------------------------------------------------
     def time_embedding(self, t_dev, batch, aug_emb=None):
-        """t_dev: fp32 device tensor [1]. Returns the per-resnet time_emb_proj outputs [batch, sum(Cout)]."""
+        """t_dev: fp32 device tensor with 1 value (broadcast to `batch` rows) or `batch` values (one timestep per
+        sample: the hoisted garment pass). Returns the per-resnet time_emb_proj outputs [batch, sum(Cout)]."""
         L = self.L
-        t_emb = L.timestep_embedding(t_dev, self.ch[0], rows_repeat=batch)
-        h = L.skinny_linear(t_emb, self.te[0], self.te[1], out_silu=True)
-        emb = L.skinny_linear(h, self.te[2], self.te[3], addend=aug_emb)
-        return L.skinny_linear(emb, self.temb_w, self.temb_b, in_silu=True)
+        n = t_dev.numel()
+        assert n == 1 or n == batch
+        t_emb = L.timestep_embedding(t_dev, self.ch[0], rows_repeat=batch if n == 1 else 1)
+        out = torch.empty((batch, self.temb_w.shape[0]), dtype=torch.float16, device=self.device)
+        for r0 in range(0, batch, 16):                      # the skinny-linear kernel takes <= 16 rows per launch
+            r1 = min(batch, r0 + 16)
+            h = L.skinny_linear(t_emb[r0:r1], self.te[0], self.te[1], out_silu=True)
+            emb = L.skinny_linear(h, self.te[2], self.te[3], addend=None if aug_emb is None else aug_emb[r0:r1])
+            L.skinny_linear(emb, self.temb_w, self.temb_b, in_silu=True, out=out[r0:r1])
+        return out
 
     def _resnet(self, r, x0, x1, temb_all):
         L = self.L
@@ -269,9 +276,18 @@ class UNetEngine:
         assert x1 is None
         return L.conv3x3(h, r.w2, bias=r.b2, residual=x0)
 
-    def _block(self, blk, h, B, N, ctx, gfeat, n_persons, collect):
+    def garment_kv(self, blk, gfeat, out=None):
+        """K/V of garment tokens as the TRY-ON UNet sees them: attn1.to_k / to_v applied to the garment UNet's
+        post-norm1 feature (src/attentionhacked_tryon.py:334 + ip_adapter/attention_processor.py:247-248).
+        gfeat [n, Ng, C] -> [n, Ng, 2C] = [K | V]."""
+        n, ng, C = gfeat.shape
+        o2 = None if out is None else out.view(n * ng, 2 * C)
+        return self.L.gemm(gfeat.reshape(n * ng, C), blk.wqkv[C:], out=o2).view(n, ng, 2 * C)
+
+    def _block(self, blk, h, B, N, ctx, gfeat, n_persons, collect, gkv_pre=None):
         """h: [B*N, C]. gfeat: garment feature for this block ([Bg,Ng,C], try-on fast path), a full [B,Ng,C] tensor
-        (reference-format features through the module seam) or None (garment UNet)."""
+        (reference-format features through the module seam) or None (garment UNet). gkv_pre = (kv [T*Bg,Ng,2C],
+        n_garments, step_base int32 device scalar): garment K/V precomputed for all denoise steps."""
         L = self.L
         C, H = blk.c, blk.heads
         n1 = L.layernorm(h, blk.ln1w, blk.ln1b)
@@ -283,11 +299,15 @@ class UNetEngine:
                 raise _GarmentDone()
         qkv = L.gemm(n1, blk.wqkv).view(B, N, 3 * C)
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-        if gfeat is None:
+        if gkv_pre is not None:
+            kv_all, n_g, base = gkv_pre
+            a = L.attention(q, k, v, kv_all[..., :C], kv_all[..., C:], kv1_off=n_persons, heads=H, kv1_mod=n_g,
+                            kv1_base=base)
+        elif gfeat is None:
             a = L.attention(q, k, v, heads=H)
         else:
             bg, ng, _ = gfeat.shape
-            gkv = L.gemm(gfeat.reshape(bg * ng, C), blk.wqkv[C:]).view(bg, ng, 2 * C)
+            gkv = self.garment_kv(blk, gfeat)
             off = 0 if bg == B else n_persons       # full-format features: every sample has its own segment 1
             a = L.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=off, heads=H)
         h = L.gemm(a.view(B * N, C), blk.wo1, bias=blk.bo1, residual=h)
@@ -312,24 +332,27 @@ class UNetEngine:
         for blk in t.blocks:
             i = state["idx"]
             gf = state["gfeats"][i] if state["gfeats"] is not None else None
-            h = self._block(blk, h, B, N, state["ctx"][i], gf, state["n_persons"], state["collect"])
+            gp = None
+            if state["gkv_pre"] is not None:
+                gp = (state["gkv_pre"][0][i], state["gkv_pre"][1], state["gkv_pre"][2])
+            h = self._block(blk, h, B, N, state["ctx"][i], gf, state["n_persons"], state["collect"], gp)
             state["idx"] = i + 1
         out = L.gemm(h, t.wout, bias=t.bout, residual=x.view(B * N, C))
         return out.view(B, Hh, Ww, C)
 
-    def forward(self, x_in, temb_all, ctx, gfeats=None, n_persons=0, collect=None):
+    def forward(self, x_in, temb_all, ctx, gfeats=None, n_persons=0, collect=None, gkv_pre=None):
         """x_in: [B,h,w,64] NHWC fp16 (input channels zero-padded). Returns the try-on eps [B,h,w,16] (first
         out_channels valid) or, for the garment UNet, None (features are appended to `collect`)."""
         try:
-            return self._forward(x_in, temb_all, ctx, gfeats, n_persons, collect)
+            return self._forward(x_in, temb_all, ctx, gfeats, n_persons, collect, gkv_pre)
         except _GarmentDone:
             return None
 
-    def _forward(self, x_in, temb_all, ctx, gfeats, n_persons, collect):
+    def _forward(self, x_in, temb_all, ctx, gfeats, n_persons, collect, gkv_pre=None):
         L = self.L
         cfg = self.cfg
         n_lvl = len(self.ch)
-        state = dict(idx=0, ctx=ctx, gfeats=gfeats, n_persons=n_persons, collect=collect)
+        state = dict(idx=0, ctx=ctx, gfeats=gfeats, n_persons=n_persons, collect=collect, gkv_pre=gkv_pre)
         x = L.conv3x3(x_in, self.w_in, bias=self.b_in)
         skips = [x]
         for i, lvl in enumerate(self.down):

@@ -19,7 +19,8 @@ SIGNATURES = {
     "b200vton_gemm_f16": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
     "b200vton_conv3x3_nhwc": [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64,
                               _vp, _i64, _i, _vp],
-    "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i,
+                           _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
     "b200vton_nchw_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -141,7 +142,8 @@ def conv3x3(x, w_packed, bias=None, temb=None, sc0=None, sc1=None, w_sc=None, bi
     return out
 
 
-def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=None, accumulate=False, out=None):
+def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=None, accumulate=False, out=None,
+              kv1_mod=0, kv1_base=None):
     """q: [B,Nq,*], k0/v0: [B,N0,*], k1/v1: [B1,N1,*] 3-D views with contiguous last dim (row strides may exceed
     heads*64, e.g. slices of a fused QKV buffer). n1 > 0 with k1 None => all-zero segment-1 tokens for every sample."""
     lib = load()
@@ -161,7 +163,8 @@ def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=No
         ld1 = k1.stride(1)
         assert k1.stride(2) == 1 and k1.stride(0) == n1 * ld1 and v1.stride() == k1.stride()
     rc = lib.b200vton_attention(_p(q), q.stride(1), _p(k0), _p(v0), k0.stride(1), _p(k1), _p(v1), ld1, _p(out),
-                                out.stride(1), B, H, Nq, N0, n1, B1, kv1_off, float(scale), int(accumulate), _stream())
+                                out.stride(1), B, H, Nq, N0, n1, B1, kv1_off, kv1_mod, _p(kv1_base), float(scale),
+                                int(accumulate), _stream())
     _check(rc, "b200vton_attention")
     return out
 

@@ -57,7 +57,9 @@ int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int C
                           int64_t ldr, void* out, int64_t ldo, int force_bn, void* stream);
 
 /* softmax(Q K^T * scale) V, head_dim 64, keys/values streamed from two segments without concatenation:
- * segment 0 = (k0, v0)[b]; segment 1 = (k1, v1)[(b - kv1_off) % B1] for b >= kv1_off, and for b < kv1_off the N1
+ * segment 0 = (k0, v0)[b]; segment 1 = (k1, v1)[base + (b - kv1_off) % mod] for b >= kv1_off, where mod = kv1_mod
+ * (or B1 when kv1_mod == 0) and base = *kv1_base (a device int32, or 0 when NULL: lets one captured graph walk the
+ * per-timestep slices of garment K/V precomputed for all denoise steps); for b < kv1_off the N1
  * tokens are all-zero K/V handled in closed form (CFG-uncond half, src/tryon_pipeline.py:1796).
  * Replaces cat + F.scaled_dot_product_attention of src/attentionhacked_tryon.py:334-348 /
  * ip_adapter/attention_processor.py:238-262 (attn1) and :1970-1995 (attn2: call once for the 77 text tokens, once for
@@ -66,7 +68,8 @@ int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int C
  * q: [B,Nq,*] row stride ldq, head h at columns [64h, 64h+64); same for k/v/out. */
 int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v0, int64_t ldkv0, const void* k1,
                        const void* v1, int64_t ldkv1, void* out, int64_t ldo, int B, int H, int Nq, int N0, int N1,
-                       int B1, int kv1_off, float scale, int accumulate, void* stream);
+                       int B1, int kv1_off, int kv1_mod, const void* kv1_base, float scale, int accumulate,
+                       void* stream);
 
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
  * fp32 statistics (deterministic two-stage reduction, no atomics), optional SiLU, fp16 out [B*HW, C0+C1].

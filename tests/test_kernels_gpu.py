@@ -378,3 +378,19 @@ def test_attention_pingpong_lazy_rescale(lib):
     finally:
         lib.set_option("attention_pingpong", 1)
     close(out, out1, tol=4e-3)
+
+
+def test_attention_per_step_kv_base(lib):
+    """Hoisted garment K/V: segment 1 lives in a [T*Bg, Ng, C] tensor and a device scalar selects the timestep slice."""
+    Bp, H, N, Ng, T = 2, 4, 256, 256, 3
+    C = H * 64
+    q, k, v = rnd(2 * Bp, N, C, seed=1), rnd(2 * Bp, N, C, seed=2), rnd(2 * Bp, N, C, seed=3)
+    gkv = rnd(T * Bp, Ng, 2 * C, seed=4)
+    for step in range(T):
+        base = torch.tensor([step * Bp], dtype=torch.int32, device="cuda")
+        out = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H, kv1_mod=Bp, kv1_base=base)
+        sl = gkv[step * Bp:(step + 1) * Bp]
+        ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], sl[..., :C]], 1), torch.cat([v[Bp:], sl[..., C:]], 1), H, 0.125)
+        ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
+        close(out[Bp:], ref_c, tol=3e-3)
+        close(out[:Bp], ref_u, tol=3e-3)
