@@ -174,10 +174,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
+      // software-pipelined over the chunks: the TMEM loads of chunk c+1 are in flight while chunk c is converted,
+      // staged and stored (fully unrolled so both register buffers are statically indexed)
+      uint32_t ra[2][32], rb[2][32];
+      epilogue_load<BN, GEGLU>(p, t_row, 0, 0, ra[0], rb[0]);
+#pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < NCHUNK) epilogue_load<BN, GEGLU>(p, t_row, 0, c + 1, ra[(c + 1) & 1], rb[(c + 1) & 1]);
         uint32_t pk[16];
-        epilogue_chunk<BN, GEGLU>(p, t_row, 0, n_tile, out_row, sample, c, pk);
+        epilogue_math<BN, GEGLU>(p, n_tile, out_row, sample, c, ra[c & 1], rb[c & 1], pk);
         uint8_t* dst = my_stage_gen + c * 2048 + lane * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q)

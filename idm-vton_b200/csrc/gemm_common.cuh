@@ -58,21 +58,24 @@ __device__ __forceinline__ void map_row(const GemmParams& p, int m_tile, int r_l
 // shortcut, residual with the reference's fp16 rounding points) -> 16 packed half2 words. Warp-collective
 // (tcgen05.ld). t_row: TMEM address (lane quarter | column base of accumulator 0); the shortcut accumulator (if any)
 // sits sc_col_off columns further. Columns >= N of the last tile carry don't-care values (the sinks clip them).
+// issue the TMEM loads of chunk c (no wait): accumulator 0 into acc, the gate half / shortcut accumulator into acc2
 template <int BN, bool GEGLU>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
-                                               long long out_row, int sample, int c, uint32_t (&pk)[16]) {
-  const int n0 = n_tile * BN;
-  const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
-  const int out_N = GEGLU ? p.N / 2 : p.N;
-  uint32_t acc[32];
-  uint32_t acc2[32];
+__device__ __forceinline__ void epilogue_load(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int c,
+                                              uint32_t (&acc)[32], uint32_t (&acc2)[32]) {
   tmem_ld_32x32(t_row + c * 32, acc);
   if (GEGLU) {
     tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
   } else if (p.slabs_sc) {
     tmem_ld_32x32(t_row + sc_col_off + c * 32, acc2);
   }
-  tmem_ld_wait();
+}
+
+template <int BN, bool GEGLU>
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, long long out_row, int sample, int c,
+                                              const uint32_t (&acc)[32], const uint32_t (&acc2)[32], uint32_t (&pk)[16]) {
+  const int n0 = n_tile * BN;
+  const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
+  const int out_N = GEGLU ? p.N / 2 : p.N;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
@@ -164,6 +167,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_r
     pk[g * 4 + 2] = pack_h2(v[4], v[5]);
     pk[g * 4 + 3] = pack_h2(v[6], v[7]);
   }
+}
+
+template <int BN, bool GEGLU>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
+                                               long long out_row, int sample, int c, uint32_t (&pk)[16]) {
+  uint32_t acc[32];
+  uint32_t acc2[32];
+  epilogue_load<BN, GEGLU>(p, t_row, sc_col_off, c, acc, acc2);
+  tmem_ld_wait();
+  epilogue_math<BN, GEGLU>(p, n_tile, out_row, sample, c, acc, acc2, pk);
 }
 
 // Sink 1 (1-CTA kernel): registers -> global, each thread writes its own row.

@@ -40,28 +40,37 @@ class TryOnDenoiser:
         B, _, h, w = latents.shape
         Bt = 2 * B if do_cfg else B
         Bg = cloth_latents.shape[0]
+        dev = self.device
+        key = (B, Bt, Bg, h, w, bool(do_cfg), tuple(prompt_embeds.shape), tuple(image_embeds.shape),
+               tuple(text_embeds_cloth.shape))
+        fresh = key != getattr(self, "_key", None)
+        self._key = key
         self.B, self.Bt, self.Bg, self.h, self.w = B, Bt, Bg, h, w
         self.do_cfg = do_cfg
         self.guidance_scale = float(guidance_scale)
-        dev = self.device
-        self._graph = None
-        self.latents = latents.to(dev, f16).contiguous().clone()
-        self.latents_next = torch.empty_like(self.latents)
-        self.noise = torch.zeros_like(self.latents)
-        self.x_t = torch.zeros((Bt, h, w, CIN_PAD), dtype=f16, device=dev)
+        if fresh:
+            # (re)allocate every static buffer the step graph points at; same-shaped requests reuse them (and the
+            # captured graph) and only overwrite their contents
+            self._graph = None
+            self.gkv_all = None
+            self.latents = torch.empty((B, 4, h, w), dtype=f16, device=dev)
+            self.latents_next = torch.empty_like(self.latents)
+            self.noise = torch.zeros_like(self.latents)
+            self.x_t = torch.zeros((Bt, h, w, CIN_PAD), dtype=f16, device=dev)
+            self.x_g = torch.zeros((Bg, h, w, CIN_PAD), dtype=f16, device=dev)
+            self.t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.coef = torch.zeros(6, dtype=torch.float32, device=dev)
+            self.step_base = torch.zeros(1, dtype=torch.int32, device=dev)   # step index * Bg (hoisted garment K/V)
+            self.ctx_t = self.ctx_g = self.aug = None
+            self.eps = None
+        self.latents.copy_(latents.to(dev, f16))
         L.nchw_to_nhwc(mask.to(dev, f16).contiguous(), self.x_t, c_off=4)
         L.nchw_to_nhwc(masked_image_latents.to(dev, f16).contiguous(), self.x_t, c_off=5)
         L.nchw_to_nhwc(pose_latents.to(dev, f16).contiguous(), self.x_t, c_off=9)
-        self.x_g = torch.zeros((Bg, h, w, CIN_PAD), dtype=f16, device=dev)
         L.nchw_to_nhwc(cloth_latents.to(dev, f16).contiguous(), self.x_g, c_off=0)
-        self.ctx_t = self.tryon.encode_context(prompt_embeds.to(dev, f16), image_embeds.to(dev, f16))
-        self.ctx_g = self.garment.encode_context(text_embeds_cloth.to(dev, f16))
-        self.aug = self.tryon.aug_embedding(add_text_embeds.to(dev, f16), add_time_ids.to(dev))
-        self.t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.coef = torch.zeros(6, dtype=torch.float32, device=dev)
-        self.step_base = torch.zeros(1, dtype=torch.int32, device=dev)     # = step index * Bg (hoisted garment K/V)
-        self.eps = None
-        self.gkv_all = None
+        self.ctx_t = self.tryon.encode_context(prompt_embeds.to(dev, f16), image_embeds.to(dev, f16), out=self.ctx_t)
+        self.ctx_g = self.garment.encode_context(text_embeds_cloth.to(dev, f16), out=self.ctx_g)
+        self.aug = self.tryon.aug_embedding(add_text_embeds.to(dev, f16), add_time_ids.to(dev), out=self.aug)
 
     def set_step_tables(self, scheduler, timesteps):
         """Uploads the per-step scalars: t and {gs, sqrt(1-abar), 1/sqrt(abar), c0, c1, sigma}."""
@@ -80,8 +89,11 @@ class TryOnDenoiser:
         L = self.L
         T, Bg = self.t_table.numel(), self.Bg
         blocks = self.tryon.blocks()
+        gkv = self.gkv_all            # buffers of an earlier same-shaped request are overwritten in place
+        if gkv is not None and gkv[0].shape[0] != T * Bg:
+            gkv = None
+            self._graph = None
         self.gkv_all = None
-        gkv = None
         for c0 in range(0, T, self.garment_chunk):
             n = min(self.garment_chunk, T - c0)
             t_rows = self.t_table[c0:c0 + n].repeat_interleave(Bg).contiguous()            # timestep-major rows

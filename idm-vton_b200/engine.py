@@ -222,9 +222,10 @@ class UNetEngine:
     # -------------------------------------------------------------------------------------------
     # step-invariant precompute (once per request): cross-attention K/V, aug_emb
     # -------------------------------------------------------------------------------------------
-    def encode_context(self, text, ip=None):
+    def encode_context(self, text, ip=None, out=None):
         """text: [Bt,77,cross] fp16, ip: [Bt,16,cross] fp16 (Resampler output). Returns per-block (kv_txt, kv_ip),
-        each [Bt, T, 2C] = [K | V] produced by attn2.to_k/to_v (and the processor's to_k_ip/to_v_ip)."""
+        each [Bt, T, 2C] = [K | V] produced by attn2.to_k/to_v (and the processor's to_k_ip/to_v_ip). `out`: a list
+        returned by an earlier call with the same shapes, overwritten in place (keeps a captured graph valid)."""
         L = self.L
         bt, nt, _ = text.shape
         t2 = text.reshape(bt * nt, -1).to(torch.float16).contiguous()
@@ -232,13 +233,17 @@ class UNetEngine:
         if ip is not None and self.ip_tokens:
             i2 = ip.reshape(bt * ip.shape[1], -1).to(torch.float16).contiguous()
         ctx = []
-        for blk in self.blocks():
-            kv_t = L.gemm(t2, blk.wkv_txt).view(bt, nt, 2 * blk.c)
-            kv_i = L.gemm(i2, blk.wkv_ip).view(bt, ip.shape[1], 2 * blk.c) if i2 is not None else None
+        for j, blk in enumerate(self.blocks()):
+            o_t = out[j][0].view(bt * nt, 2 * blk.c) if out is not None else None
+            kv_t = L.gemm(t2, blk.wkv_txt, out=o_t).view(bt, nt, 2 * blk.c)
+            kv_i = None
+            if i2 is not None:
+                o_i = out[j][1].view(bt * ip.shape[1], 2 * blk.c) if out is not None else None
+                kv_i = L.gemm(i2, blk.wkv_ip, out=o_i).view(bt, ip.shape[1], 2 * blk.c)
             ctx.append((kv_t, kv_i))
         return ctx
 
-    def aug_embedding(self, text_embeds, time_ids):
+    def aug_embedding(self, text_embeds, time_ids, out=None):
         """add_embedding(concat(text_embeds, Timesteps(time_ids))) — step-invariant (src/unet_hacked_tryon.py:1174-1190)."""
         L = self.L
         b = text_embeds.shape[0]
@@ -246,7 +251,7 @@ class UNetEngine:
         te = L.timestep_embedding(time_ids.flatten().to(torch.float32).contiguous(), dim).view(b, -1)
         add = torch.cat([text_embeds.to(torch.float16), te], dim=-1).contiguous()
         h = L.skinny_linear(add, self.ae[0], self.ae[1], out_silu=True)
-        return L.skinny_linear(h, self.ae[2], self.ae[3])
+        return L.skinny_linear(h, self.ae[2], self.ae[3], out=out)
 
     # -------------------------------------------------------------------------------------------
     # per-step pieces

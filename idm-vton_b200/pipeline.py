@@ -110,6 +110,8 @@ class StableDiffusionXLInpaintPipeline:
             if m is not None and hasattr(m, "to"):
                 m.to(device) if dtype is None else m.to(device=device, dtype=dtype)
         self._denoiser = None
+        self._vae_fp32 = None
+        self._uncond_clip_key = None
         return self
 
     @property
@@ -190,8 +192,13 @@ class StableDiffusionXLInpaintPipeline:
         if output_hidden_states:
             hs = self.image_encoder(image, output_hidden_states=True).hidden_states[-2]
             hs = hs.repeat_interleave(num_images_per_prompt, dim=0)
-            un = self.image_encoder(torch.zeros_like(image), output_hidden_states=True).hidden_states[-2]
-            un = un.repeat_interleave(num_images_per_prompt, dim=0)
+            # the unconditional branch encodes an all-zero image: the same tensor for every call with this encoder,
+            # so it is computed once per (shape, dtype, device) and reused
+            key = (tuple(image.shape), image.dtype, str(image.device))
+            if getattr(self, "_uncond_clip_key", None) != key:
+                self._uncond_clip = self.image_encoder(torch.zeros_like(image), output_hidden_states=True).hidden_states[-2]
+                self._uncond_clip_key = key
+            un = self._uncond_clip.repeat_interleave(num_images_per_prompt, dim=0)
             return hs, un
         emb = self.image_encoder(image).image_embeds.repeat_interleave(num_images_per_prompt, dim=0)
         return emb, torch.zeros_like(emb)
@@ -317,19 +324,31 @@ class StableDiffusionXLInpaintPipeline:
         if padding_mask_crop is not None:
             raise ValueError("padding_mask_crop is not supported by the B200 engine pipeline (not used by inference.py)")
 
+    def _vae32(self):
+        """fp32 twin of the VAE for the reference's force_upcast path (src/tryon_pipeline.py:913-915,1076-1093).
+        The reference flips the one VAE between fp16 and fp32 around every use; keeping a persistent fp32 copy is the
+        same arithmetic without converting 84M parameters eight times per call."""
+        if self.vae.dtype == torch.float32:
+            return self.vae
+        twin = getattr(self, "_vae_fp32", None)
+        if twin is None or twin[0] is not self.vae or twin[1].device != self.vae.device:
+            import copy
+            twin = (self.vae, copy.deepcopy(self.vae).to(dtype=torch.float32))
+            self._vae_fp32 = twin
+        return twin[1]
+
     def _encode_vae_image(self, image, generator):
         """src/tryon_pipeline.py:911-932."""
         dtype = image.dtype
+        vae = self.vae
         if self.vae.config.force_upcast:
             image = image.float()
-            self.vae.to(dtype=torch.float32)
+            vae = self._vae32()
         if isinstance(generator, list):
-            image_latents = torch.cat([retrieve_latents(self.vae.encode(image[i:i + 1]), generator=generator[i])
+            image_latents = torch.cat([retrieve_latents(vae.encode(image[i:i + 1]), generator=generator[i])
                                        for i in range(image.shape[0])], dim=0)
         else:
-            image_latents = retrieve_latents(self.vae.encode(image), generator=generator)
-        if self.vae.config.force_upcast:
-            self.vae.to(dtype)
+            image_latents = retrieve_latents(vae.encode(image), generator=generator)
         return self.vae.config.scaling_factor * image_latents.to(dtype)
 
     def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None,
@@ -602,12 +621,8 @@ class StableDiffusionXLInpaintPipeline:
 
         if not output_type == "latent":
             needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
-            if needs_upcasting:
-                self.vae.to(dtype=torch.float32)
-                latents = latents.to(torch.float32)
-            image = self.vae.decode(latents.to(self.vae.dtype) / self.vae.config.scaling_factor, return_dict=False)[0]
-            if needs_upcasting:
-                self.vae.to(dtype=torch.float16)
+            vae = self._vae32() if needs_upcasting else self.vae
+            image = vae.decode(latents.to(vae.dtype) / self.vae.config.scaling_factor, return_dict=False)[0]
         # NB (reference quirk, src/tryon_pipeline.py:1868-1885): with output_type == "latent", `image` is still the
         # caller's input image, and that is what gets returned.
         image = self.image_processor.postprocess(image, output_type=output_type)

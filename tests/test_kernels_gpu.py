@@ -394,3 +394,21 @@ def test_attention_per_step_kv_base(lib):
         ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
         close(out[Bp:], ref_c, tol=3e-3)
         close(out[:Bp], ref_u, tol=3e-3)
+
+
+def test_attention_fp16_exp_vs_fp32_softmax(lib):
+    """The packed-half softmax kernel (attn3.cu) against the fp32-softmax ping-pong kernel (attn2.cu) and the fp32
+    reference, on a diffuse and on a peaky score distribution."""
+    B, H, N = 2, 4, 1024
+    C = H * 64
+    for qscale in (1.0, 4.0):
+        q, k, v = rnd(B, N, C, scale=qscale, seed=1), rnd(B, N, C, seed=2), rnd(B, N, C, seed=3)
+        ref = _attn_ref(q, k, v, H, 0.125)
+        o3 = lib.attention(q, k, v, heads=H)
+        lib.set_option("attention_fp16_exp", 0)
+        try:
+            o2 = lib.attention(q, k, v, heads=H)
+        finally:
+            lib.set_option("attention_fp16_exp", 1)
+        e3, e2 = close(o3, ref, tol=4e-3), close(o2, ref, tol=4e-3)
+        print(f"qscale {qscale}: fp16-exp err {e3:.2e}, fp32-softmax err {e2:.2e}")
