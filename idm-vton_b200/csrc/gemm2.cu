@@ -175,15 +175,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       // software-pipelined over the chunks: the TMEM loads of chunk c+1 are in flight while chunk c is converted,
-      // staged and stored (fully unrolled so both register buffers are statically indexed)
-      uint32_t ra[2][32], rb[2][32];
-      epilogue_load<BN, GEGLU>(p, t_row, 0, 0, ra[0], rb[0]);
-#pragma unroll
+      // staged and stored. The loop stays ROLLED with one copy of the epilogue math (the prefetched registers are moved
+      // into the working set each iteration): a full unroll made the kernel I-cache bound (ncu: stalled_no_instruction
+      // dominated, profiles/r1_ncu_notes.md).
+      uint32_t cur_a[32], cur_b[32], nxt_a[32], nxt_b[32];
+      epilogue_load<BN, GEGLU>(p, t_row, 0, 0, nxt_a, nxt_b);
+#pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
         tmem_ld_wait();
-        if (c + 1 < NCHUNK) epilogue_load<BN, GEGLU>(p, t_row, 0, c + 1, ra[(c + 1) & 1], rb[(c + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          cur_a[i] = nxt_a[i];
+          cur_b[i] = nxt_b[i];
+        }
+        if (c + 1 < NCHUNK) epilogue_load<BN, GEGLU>(p, t_row, 0, c + 1, nxt_a, nxt_b);
         uint32_t pk[16];
-        epilogue_math<BN, GEGLU>(p, n_tile, out_row, sample, c, ra[c & 1], rb[c & 1], pk);
+        epilogue_math<BN, GEGLU, false>(p, n_tile, out_row, sample, c, cur_a, cur_b, pk);
         uint8_t* dst = my_stage_gen + c * 2048 + lane * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q)

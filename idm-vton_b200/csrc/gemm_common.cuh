@@ -70,7 +70,7 @@ __device__ __forceinline__ void epilogue_load(const GemmParams& p, uint32_t t_ro
   }
 }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, bool HAS_SC = true>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, long long out_row, int sample, int c,
                                               const uint32_t (&acc)[32], const uint32_t (&acc2)[32], uint32_t (&pk)[16]) {
   const int n0 = n_tile * BN;
@@ -120,8 +120,8 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
           v[2 * j + 1] += a.y;
         }
       }
-      if (p.act_gelu) {
-#pragma unroll
+      if (p.act_gelu) {   // rare (Resampler FeedForward): keep it rolled, erff is ~40 instructions
+#pragma unroll 1
         for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
       }
       if (p.rowvec && col_ok) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
           v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
         }
       }
-      if (p.slabs_sc) {
+      if (HAS_SC && p.slabs_sc) {
         float s[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
