@@ -8,9 +8,10 @@
 // double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> fp16 -> swizzled smem ->
 // per-warp TMA stores) overlaps the main loop of tile i+1.
 //   warp 0: TMA producer (both CTAs)      warp 1: MMA issuer (leader CTA) + TMEM alloc (both)
-//   warps 2..5: epilogue (both CTAs, thread = accumulator row of the CTA's own 128-row half)
+//   warps 2..9: epilogue (both CTAs; thread = accumulator row of the CTA's own 128-row half; the two warps that share a
+//               TMEM lane quarter take the even / odd 32-column chunks of the tile)
 // Barriers: full[s] lives in the leader (both CTAs' TMA bytes are credited to it), empty[s] / tmem_full[a] are
-// multicast-committed to both CTAs, tmem_empty[a] lives in the leader and collects one arrive per epilogue warp (8).
+// multicast-committed to both CTAs, tmem_empty[a] lives in the leader and collects one arrive per epilogue warp (16).
 #include "gemm_common.cuh"
 #include "host.h"
 
@@ -22,13 +23,14 @@ struct Smem2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging: per warp one 32-row x 32-column fp16 buffer (2 KB, 64B-swizzled) per chunk of the tile
   static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STORE_BYTES = 4 * (BN / 32) * 2048;
+  static constexpr int RING = (BN / 32 + 1) / 2;             // chunks handled by one epilogue warp per tile
+  static constexpr int STORE_BYTES = 8 * RING * 2048;
   static constexpr int BAR_OFFSET = STORE_OFFSET + STORE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
-template <int BN, int STAGES, bool GEGLU>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int STAGES, bool GEGLU, int EPI>
+__global__ void __launch_bounds__(320, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const GemmParams p, int m_pairs) {
   using L = Smem2<BN, STAGES>;
@@ -62,7 +64,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);   // 4 epilogue warps x 2 CTAs
+      mbar_init(tempty_bar(a), 16);   // 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -143,10 +145,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // epilogue needs no CTA-wide barrier and never waits for a store inside a tile: the buffers are only recycled at
     // the next tile, a full main loop later. Rows / columns outside the output are clipped by the tensor map.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;            // 0: even chunks, 1: odd chunks
     const int row = quarter * 32 + lane;
     constexpr int OUT_COLS = GEGLU ? BN / 2 : BN;
     constexpr int NCHUNK = OUT_COLS / 32;
-    const uint32_t my_stage = smem_base + L::STORE_OFFSET + quarter * (NCHUNK * 2048);
+    const uint32_t my_stage = smem_base + L::STORE_OFFSET + (half * 4 + quarter) * (L::RING * 2048);
     uint8_t* my_stage_gen = smem_raw + (my_stage - smem_u32(smem_raw));
     const int sw = (lane >> 1) & 3;
     // origin of this warp's 32 accumulator rows inside the conv tile box (rows are ordered x fastest, then y, then b)
@@ -174,24 +177,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      // software-pipelined over the chunks: the TMEM loads of chunk c+1 are in flight while chunk c is converted,
-      // staged and stored. The loop stays ROLLED with one copy of the epilogue math (the prefetched registers are moved
-      // into the working set each iteration): a full unroll made the kernel I-cache bound (ncu: stalled_no_instruction
-      // dominated, profiles/r1_ncu_notes.md).
-      uint32_t cur_a[32], cur_b[32], nxt_a[32], nxt_b[32];
-      epilogue_load<BN, GEGLU>(p, t_row, 0, 0, nxt_a, nxt_b);
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          cur_a[i] = nxt_a[i];
-          cur_b[i] = nxt_b[i];
-        }
-        if (c + 1 < NCHUNK) epilogue_load<BN, GEGLU>(p, t_row, 0, c + 1, nxt_a, nxt_b);
+      for (int c = half; c < NCHUNK; c += 2) {
         uint32_t pk[16];
-        epilogue_math<BN, GEGLU, false>(p, n_tile, out_row, sample, c, cur_a, cur_b, pk);
-        uint8_t* dst = my_stage_gen + c * 2048 + lane * 64;
+        epilogue_chunk<BN, GEGLU, EPI>(p, t_row, 0, n_tile, out_row, sample, c, pk);
+        const uint32_t slot = (c >> 1) * 2048;
+        uint8_t* dst = my_stage_gen + slot + lane * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(dst + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -199,9 +190,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) {
           if (p.conv)
-            tma_store_4d(&tmOut, my_stage + c * 2048, out_n0 + c * 32, x0 + qx, y0 + qy, b0 + qb);
+            tma_store_4d(&tmOut, my_stage + slot, out_n0 + c * 32, x0 + qx, y0 + qy, b0 + qb);
           else
-            tma_store_2d(&tmOut, my_stage + c * 2048, out_n0 + c * 32, m_tile * BM + quarter * 32);
+            tma_store_2d(&tmOut, my_stage + slot, out_n0 + c * 32, m_tile * BM + quarter * 32);
           tma_store_commit();
         }
       }
@@ -223,11 +214,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool GEGLU>
+template <int BN, int STAGES, bool GEGLU, int EPI>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmParams& p,
                    int m_pairs, cudaStream_t stream) {
   using L = Smem2<BN, STAGES>;
-  auto kern = gemm2_kernel<BN, STAGES, GEGLU>;
+  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI>;
   static bool configured = false;
   if (!configured) {
     VTON_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -237,7 +228,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const int clusters = tiles < kSMs / 2 ? tiles : kSMs / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -277,18 +268,33 @@ int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap
     uint32_t box[2] = {32, 32};
     if (int e = encode_tmap_f16(&tmOut, p.out, 2, dims, strides, box, nullptr, 64)) return e;
   }
+  // epilogue specialisation: the four combinations the UNets use get their own kernels, anything else is generic
+  int epi = (p.bias ? EPI_BIAS : 0) | (p.rowvec ? EPI_ROWVEC : 0) | (p.residual ? EPI_RES : 0);
+  if (p.act_gelu || !(epi == 0 || epi == EPI_BIAS || epi == (EPI_BIAS | EPI_ROWVEC) || epi == (EPI_BIAS | EPI_RES)))
+    epi = EPI_RUNTIME;
   if (geglu) {
-    if (bn == 256) return launch2<256, 5, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-    if (bn == 128) return launch2<128, 7, true>(tmA, tmB, tmOut, p, m_pairs, stream);
+    if (bn == 256) return launch2<256, 5, true, 0>(tmA, tmB, tmOut, p, m_pairs, stream);
+    if (bn == 128) return launch2<128, 7, true, 0>(tmA, tmB, tmOut, p, m_pairs, stream);
     set_last_error("gemm2: GEGLU epilogue supports BN 128/256 only (got %d)", bn);
     return kErrUnsupported;
   }
-  switch (bn) {
-    case 128: return launch2<128, 7, false>(tmA, tmB, tmOut, p, m_pairs, stream);
-    case 160: return launch2<160, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
-    case 192: return launch2<192, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
-    case 256: return launch2<256, 5, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+#define VTON_G2(BN_, ST_)                                                                                  \
+  switch (epi) {                                                                                           \
+    case 0: return launch2<BN_, ST_, false, 0>(tmA, tmB, tmOut, p, m_pairs, stream);                        \
+    case EPI_BIAS: return launch2<BN_, ST_, false, EPI_BIAS>(tmA, tmB, tmOut, p, m_pairs, stream);           \
+    case EPI_BIAS | EPI_ROWVEC:                                                                              \
+      return launch2<BN_, ST_, false, EPI_BIAS | EPI_ROWVEC>(tmA, tmB, tmOut, p, m_pairs, stream);           \
+    case EPI_BIAS | EPI_RES:                                                                                 \
+      return launch2<BN_, ST_, false, EPI_BIAS | EPI_RES>(tmA, tmB, tmOut, p, m_pairs, stream);              \
+    default: return launch2<BN_, ST_, false, EPI_RUNTIME>(tmA, tmB, tmOut, p, m_pairs, stream);              \
   }
+  switch (bn) {
+    case 128: VTON_G2(128, 7)
+    case 160: VTON_G2(160, 6)
+    case 192: VTON_G2(192, 6)
+    case 256: VTON_G2(256, 5)
+  }
+#undef VTON_G2
   set_last_error("gemm2: unsupported BN %d", bn);
   return kErrUnsupported;
 }

@@ -54,28 +54,77 @@ __device__ __forceinline__ void map_row(const GemmParams& p, int m_tile, int r_l
   }
 }
 
-// One 32-column chunk of the fused epilogue for one accumulator row: TMEM -> registers -> (bias, activation, temb,
-// shortcut, residual with the reference's fp16 rounding points) -> 16 packed half2 words. Warp-collective
-// (tcgen05.ld). t_row: TMEM address (lane quarter | column base of accumulator 0); the shortcut accumulator (if any)
-// sits sc_col_off columns further. Columns >= N of the last tile carry don't-care values (the sinks clip them).
+// Epilogue specialisation (compile time): which terms exist. EPI_RUNTIME keeps every term behind a runtime test of the
+// GemmParams pointers (1-CTA kernel, rare combinations); the others strip the unused code so the epilogue warps —
+// one per scheduler — execute ~100 instead of ~1000 instructions per 32-column chunk (ncu, profiles/r1_ncu_notes.md).
+enum : int { EPI_BIAS = 1, EPI_ROWVEC = 2, EPI_RES = 4, EPI_RUNTIME = 8 };
+
+// erf-GELU with the Abramowitz-Stegun 7.1.26 rational/exponential form (|abs err| < 2e-7, far below the fp16 rounding
+// that follows): ~16 instructions instead of erff's ~40.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  const float arg = -ax * ax * 1.4426950408889634f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
+
 // issue the TMEM loads of chunk c (no wait): accumulator 0 into acc, the gate half / shortcut accumulator into acc2
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int EPI>
 __device__ __forceinline__ void epilogue_load(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int c,
                                               uint32_t (&acc)[32], uint32_t (&acc2)[32]) {
   tmem_ld_32x32(t_row + c * 32, acc);
   if (GEGLU) {
     tmem_ld_32x32(t_row + BN / 2 + c * 32, acc2);
-  } else if (p.slabs_sc) {
+  } else if ((EPI & EPI_RUNTIME) && p.slabs_sc) {
     tmem_ld_32x32(t_row + sc_col_off + c * 32, acc2);
   }
 }
 
-template <int BN, bool GEGLU, bool HAS_SC = true>
+__device__ __forceinline__ void add_h8(float (&v)[8], const __half* src) {
+  const uint4 u = *reinterpret_cast<const uint4*>(src);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_h2(w[j]);
+    v[2 * j] += a.x;
+    v[2 * j + 1] += a.y;
+  }
+}
+__device__ __forceinline__ void round_add_h8(float (&v)[8], const __half* src) {   // v = fp16(v) + src
+  const uint4 u = *reinterpret_cast<const uint4*>(src);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_h2(w[j]);
+    v[2 * j] = round_h(v[2 * j]) + a.x;
+    v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+  }
+}
+
+// One 32-column chunk of the fused epilogue for one accumulator row: registers -> (bias, activation, temb, shortcut,
+// residual with the reference's fp16 rounding points) -> 16 packed half2 words. Columns >= N of the last tile carry
+// don't-care values (the sinks clip them).
+template <int BN, bool GEGLU, int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, long long out_row, int sample, int c,
                                               const uint32_t (&acc)[32], const uint32_t (&acc2)[32], uint32_t (&pk)[16]) {
+  constexpr bool RT = (EPI & EPI_RUNTIME) != 0;
+  const bool has_bias = RT ? (p.bias != nullptr) : ((EPI & EPI_BIAS) != 0);
+  const bool has_rowvec = RT ? (p.rowvec != nullptr) : ((EPI & EPI_ROWVEC) != 0);
+  const bool has_res = RT ? (p.residual != nullptr) : ((EPI & EPI_RES) != 0);
   const int n0 = n_tile * BN;
   const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
   const int out_N = GEGLU ? p.N / 2 : p.N;
+  const __half* rowvec_row = has_rowvec ? p.rowvec + static_cast<long long>(sample) * p.ld_rowvec : nullptr;
+  const __half* res_row = (has_res && out_row >= 0) ? p.residual + out_row * p.ld_res : nullptr;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int ncol = out_n0 + c * 32 + g * 8;  // output column of this 8-group
@@ -89,78 +138,31 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
 #pragma unroll
       for (int j = 0; j < 8; ++j) gt[j] = __uint_as_float(acc2[g * 8 + j]);
       if (p.bias && col_ok) {
-        const uint4 bh = *reinterpret_cast<const uint4*>(p.bias + bcol);
-        const uint4 bg = *reinterpret_cast<const uint4*>(p.bias + bcol + BN / 2);
-        const uint32_t bhw[4] = {bh.x, bh.y, bh.z, bh.w};
-        const uint32_t bgw[4] = {bg.x, bg.y, bg.z, bg.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_h2(bhw[j]);
-          const float2 b = unpack_h2(bgw[j]);
-          v[2 * j] += a.x;
-          v[2 * j + 1] += a.y;
-          gt[2 * j] += b.x;
-          gt[2 * j + 1] += b.y;
-        }
+        add_h8(v, p.bias + bcol);
+        add_h8(gt, p.bias + bcol + BN / 2);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float hv = round_h(v[j]);
         const float gv = round_h(gt[j]);
-        v[j] = hv * round_h(gelu_erf_f(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
+        v[j] = hv * round_h(gelu_erf_fast(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
       }
     } else {
-      if (p.bias && col_ok) {
-        const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + ncol);
-        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_h2(bw[j]);
-          v[2 * j] += a.x;
-          v[2 * j + 1] += a.y;
-        }
-      }
-      if (p.act_gelu) {   // rare (Resampler FeedForward): keep it rolled, erff is ~40 instructions
+      if (has_bias && col_ok) add_h8(v, p.bias + ncol);
+      if (RT && p.act_gelu) {   // rare (Resampler FeedForward): keep it rolled
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(round_h(v[j]));
+        for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(round_h(v[j]));
       }
-      if (p.rowvec && col_ok) {
-        const uint4 tv = *reinterpret_cast<const uint4*>(p.rowvec + static_cast<long long>(sample) * p.ld_rowvec + ncol);
-        const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_h2(tw[j]);
-          v[2 * j] = round_h(v[2 * j]) + a.x;
-          v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
-        }
-      }
-      if (HAS_SC && p.slabs_sc) {
+      if (has_rowvec && col_ok) round_add_h8(v, rowvec_row + ncol);
+      if (RT && p.slabs_sc) {
         float s[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(acc2[g * 8 + j]);
-        if (p.bias_sc && col_ok) {
-          const uint4 bv = *reinterpret_cast<const uint4*>(p.bias_sc + ncol);
-          const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a = unpack_h2(bw[j]);
-            s[2 * j] += a.x;
-            s[2 * j + 1] += a.y;
-          }
-        }
+        if (p.bias_sc && col_ok) add_h8(s, p.bias_sc + ncol);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
       }
-      if (p.residual && col_ok && out_row >= 0) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol);
-        const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_h2(rw[j]);
-          v[2 * j] = round_h(v[2 * j]) + a.x;
-          v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
-        }
-      }
+      if (has_res && col_ok && res_row != nullptr) round_add_h8(v, res_row + ncol);
     }
     pk[g * 4 + 0] = pack_h2(v[0], v[1]);
     pk[g * 4 + 1] = pack_h2(v[2], v[3]);
@@ -169,14 +171,14 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
   }
 }
 
-template <int BN, bool GEGLU>
+template <int BN, bool GEGLU, int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
                                                long long out_row, int sample, int c, uint32_t (&pk)[16]) {
   uint32_t acc[32];
   uint32_t acc2[32];
-  epilogue_load<BN, GEGLU>(p, t_row, sc_col_off, c, acc, acc2);
+  epilogue_load<BN, GEGLU, EPI>(p, t_row, sc_col_off, c, acc, acc2);
   tmem_ld_wait();
-  epilogue_math<BN, GEGLU>(p, n_tile, out_row, sample, c, acc, acc2, pk);
+  epilogue_math<BN, GEGLU, EPI>(p, n_tile, out_row, sample, c, acc, acc2, pk);
 }
 
 // Sink 1 (1-CTA kernel): registers -> global, each thread writes its own row.
@@ -189,7 +191,7 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, uint32_t t_r
 #pragma unroll 1
   for (int c = 0; c < OUT_COLS / 32; ++c) {
     uint32_t pk[16];
-    epilogue_chunk<BN, GEGLU>(p, t_row, sc_col_off, n_tile, out_row, sample, c, pk);
+    epilogue_chunk<BN, GEGLU, EPI_RUNTIME>(p, t_row, sc_col_off, n_tile, out_row, sample, c, pk);
     if (out_row < 0) continue;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
