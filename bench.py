@@ -169,18 +169,42 @@ def synth_request(cfg_t, cfg_g, batch, h, w, seed, device):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------
-SAMPLE_H, SAMPLE_W = 32, 24     # latent size of the bounded CPU sample (256x192 px = 1/16 of the 768x1024 pixels)
+SAMPLE_H, SAMPLE_W = 64, 48     # latent size of the bounded CPU sample (512x384 px = 1/4 of the 768x1024 pixels)
+
+
+def usable_cpus():
+    """Host threads this process can actually run on: min(os.cpu_count, affinity mask, cgroup CPU quota). The GPU
+    boxes report 128 logical CPUs but cap the container at 16 (cpu.max = 1600000 100000); oversubscribing 128 threads
+    on that quota made the same PyTorch convolution 8x slower."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
 
 
 def cpu_reference_sample(steps, warmup, sd_src=None, log=None):
     """Times `steps` bounded samples of the reference path (oracle/unet_ref.py + loop_ref.py, CPU fp32, all host
     threads). Sample = ONE denoise step for ONE request (garment UNet batch 1 + try-on UNet batch 2 under CFG + CFG +
-    DDPM update) with the full SDXL-size UNets on a 256x192-pixel crop of the 768x1024 workload (a full-resolution
+    DDPM update) with the full SDXL-size UNets on a 512x384-pixel crop of the 768x1024 workload (a full-resolution
     step takes minutes on the host). images/sec is extrapolated by the algorithmic-FLOP ratio:
         t_image = 30 * t_sample * FLOPs(768x1024 step) / FLOPs(sample step)."""
     from oracle import loop_ref as LR
     from oracle import unet_ref as R
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     torch.set_num_threads(cores)
     cfg_t, cfg_g = R.SDXL_TRYON, R.SDXL_GARMENT
     t0 = time.time()
@@ -219,7 +243,7 @@ def cpu_reference_sample(steps, warmup, sd_src=None, log=None):
     t_sample = sum(times) / len(times)
     return dict(value=1.0 / (STEPS_DENOISE * t_sample * ratio), t_sample=t_sample, cores=cores, times=times, flop_ratio=ratio,
                 sample=f"1 denoise step (garment UNet batch 1 + try-on UNet batch 2, CFG, full SDXL-size weights) on a "
-                       f"256x192 px crop (latent {SAMPLE_H}x{SAMPLE_W}); images/sec = 1/(30 * t_sample * {ratio:.2f}) where "
+                       f"512x384 px crop (latent {SAMPLE_H}x{SAMPLE_W}); images/sec = 1/(30 * t_sample * {ratio:.2f}) where "
                        f"{ratio:.2f} = algorithmic FLOPs of a 768x1024 step / FLOPs of the sample; oracle port "
                        "(PyTorch CPU fp32, all host threads); extrapolated")
 

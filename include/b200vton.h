@@ -31,7 +31,8 @@ long long b200vton_launch_count(void);
  * problems when force_bn == 0; 0 keeps every launch on the 1-CTA kernel. "attention_pingpong" = 1 (default) runs
  * b200vton_attention on the two-tile ping-pong kernel when Nq >= 256; 0 keeps the one-tile kernel.
  * "attention_fp16_exp" = 1 (default) selects the ping-pong variant whose softmax evaluates exp2 two elements per SFU
- * op on fp16 arguments and lets the tensor core accumulate the row sums; 0 selects the fp32-softmax variant. */
+ * op on fp16 arguments and lets the tensor core accumulate the row sums; 0 selects the fp32-softmax variant.
+ * "attention_16_warps" = 1 (default) uses the variant of that kernel with 16 softmax warps per CTA. */
 int b200vton_set_option(const char* name, int value);
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear on the hot path — attn to_q/to_k/to_v/to_out

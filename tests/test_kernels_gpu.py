@@ -412,3 +412,21 @@ def test_attention_fp16_exp_vs_fp32_softmax(lib):
             lib.set_option("attention_fp16_exp", 1)
         e3, e2 = close(o3, ref, tol=4e-3), close(o2, ref, tol=4e-3)
         print(f"qscale {qscale}: fp16-exp err {e3:.2e}, fp32-softmax err {e2:.2e}")
+
+
+def test_attention_16_warp_variant_matches_8_warp(lib):
+    """attn4.cu (16 softmax warps, column-split rows, smem max exchange) vs attn3.cu on the try-on attn1 pattern."""
+    Bp, H, N, Ng = 2, 5, 640, 1000
+    C = H * 64
+    qkv = rnd(2 * Bp, N, 3 * C, seed=11)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    gkv = rnd(Bp, Ng, 2 * C, seed=12)
+    o16 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+    lib.set_option("attention_16_warps", 0)
+    try:
+        o8 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+    finally:
+        lib.set_option("attention_16_warps", 1)
+    ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
+    close(o16[Bp:], ref_c, tol=3e-3)
+    close(o16, o8, tol=2e-3)
