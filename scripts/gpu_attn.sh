@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 date > gpurun_out/attn.log
 ( timeout 420 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attention" --timeout 200 -p no:cacheprovider -x -s >> gpurun_out/attn.log 2>&1; echo "attention tests exit $?" | tee -a gpurun_out/attn.log; tail -n 8 gpurun_out/attn.log )
-( timeout 300 python - <<'PY' 2>&1 | tail -n 12
+( timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/attn_timing.log | tail -n 12
 import os, sys, json, torch
 sys.path.insert(0, ".")
 from idm_vton_b200 import lib as L
@@ -15,12 +15,12 @@ for (B, H, N, Ng, tag) in [(4, 10, 3072, 3072, "L1 self+garment"), (4, 20, 768, 
     gv = rnd(max(B // 2, 1), Ng, C) if Ng else None
     fl = 4.0 * B * H * N * N * 64 + (4.0 * (B // 2) * H * N * Ng * 64 if Ng else 0)
     res = {}
-    for name, opts in (("attn4_16warps", {"attention_16_warps": 1, "attention_fp16_exp": 1}), ("attn3_8warps", {"attention_16_warps": 0, "attention_fp16_exp": 1}), ("attn2_fp32", {"attention_fp16_exp": 0})):
+    for name, opts in (("attn5_ptmem", {"attention_p_in_tmem": 1, "attention_fp16_exp": 1}), ("attn4_16warps", {"attention_p_in_tmem": 0, "attention_16_warps": 1, "attention_fp16_exp": 1}), ("attn3_8warps", {"attention_16_warps": 0, "attention_fp16_exp": 1}), ("attn2_fp32", {"attention_fp16_exp": 0})):
         for kk, vv in opts.items():
             L.set_option(kk, vv)
         ms = timeit(lambda: L.attention(q, k, v, gk, gv, kv1_off=B // 2, heads=H))
         res[name] = round(fl / ms / 1e9, 1)
-    L.set_option("attention_16_warps", 1); L.set_option("attention_fp16_exp", 1)
+    L.set_option("attention_16_warps", 1); L.set_option("attention_fp16_exp", 1); L.set_option("attention_p_in_tmem", 1)
     print(json.dumps({"tag": tag, "tflops": res}))
 PY
 )

@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-date > gpurun_out/quick.log
-( timeout 420 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "gemm2 or 2cta or auto" --timeout 200 -p no:cacheprovider -x >> gpurun_out/quick.log 2>&1; echo "gemm2 tests exit $?" | tee -a gpurun_out/quick.log; date >> gpurun_out/quick.log; tail -n 6 gpurun_out/quick.log )
-if grep -q "gemm2 tests exit 0" gpurun_out/quick.log; then
-( MB_ONLY=gemm timeout 300 python scripts/microbench.py > gpurun_out/microbench5.log 2>&1; echo "microbench exit $?"; grep -E "gemm2|conv3x3_2cta" gpurun_out/microbench5.log | grep -vE "bn.: (128|192)" | tail -n 40 )
-fi
+( timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attention" --timeout 120 -p no:cacheprovider -x > gpurun_out/quick.log 2>&1; echo "exit $?" >> gpurun_out/quick.log; tail -n 6 gpurun_out/quick.log )
+( timeout 400 python -m pytest tests/test_engine_gpu.py -q -m gpu --timeout 200 -p no:cacheprovider -x > gpurun_out/quick_engine.log 2>&1; echo "exit $?" >> gpurun_out/quick_engine.log; tail -n 6 gpurun_out/quick_engine.log )
+( timeout 400 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err; tail -c 1500 gpurun_out/quick_bench.json )

@@ -421,12 +421,46 @@ def test_attention_16_warp_variant_matches_8_warp(lib):
     qkv = rnd(2 * Bp, N, 3 * C, seed=11)
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
     gkv = rnd(Bp, Ng, 2 * C, seed=12)
-    o16 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
-    lib.set_option("attention_16_warps", 0)
+    lib.set_option("attention_p_in_tmem", 0)
     try:
+        o16 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+        lib.set_option("attention_16_warps", 0)
         o8 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
     finally:
         lib.set_option("attention_16_warps", 1)
+        lib.set_option("attention_p_in_tmem", 1)
     ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
     close(o16[Bp:], ref_c, tol=3e-3)
     close(o16, o8, tol=2e-3)
+
+
+def test_attention_p_in_tmem_variant(lib):
+    """attn5.cu (P kept in tensor memory, TS-form P.V MMA) vs attn3.cu (P through shared memory) and the fp32 reference:
+    two segments with ragged tails, the zero-KV half, the accumulate mode and a peaky distribution."""
+    Bp, H, N, Ng = 2, 5, 640, 1000
+    C = H * 64
+    qkv = rnd(2 * Bp, N, 3 * C, seed=21)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    gkv = rnd(Bp, Ng, 2 * C, seed=22)
+    o5 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+    lib.set_option("attention_p_in_tmem", 0)
+    lib.set_option("attention_16_warps", 0)
+    try:
+        o3 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+    finally:
+        lib.set_option("attention_16_warps", 1)
+        lib.set_option("attention_p_in_tmem", 1)
+    ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
+    ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
+    close(o5[Bp:], ref_c, tol=3e-3)
+    close(o5[:Bp], ref_u, tol=3e-3)
+    close(o5, o3, tol=2e-3)
+    # peaky scores exercise the lazy rescale of O in tensor memory; long single segment exercises the stage ring wrap
+    q2, k2, v2 = rnd(1, 2048, 128, scale=4.0, seed=23), rnd(1, 2048, 128, seed=24), rnd(1, 2048, 128, seed=25)
+    close(lib.attention(q2, k2, v2, heads=2), _attn_ref(q2, k2, v2, 2, 0.125), tol=4e-3)
+    # accumulate mode (decoupled cross-attention adds the second attention onto the first)
+    base = lib.attention(q2, k2, v2, heads=2)
+    k3, v3 = rnd(1, 300, 128, seed=26), rnd(1, 300, 128, seed=27)
+    acc = base.clone()
+    lib.attention(q2, k3, v3, heads=2, out=acc, accumulate=True)
+    close(acc, base.float() + _attn_ref(q2, k3, v3, 2, 0.125), tol=4e-3)
