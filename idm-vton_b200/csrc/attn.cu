@@ -294,7 +294,12 @@ int attn5_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensor
                  int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream);
 
 static int g_attn_v2 = 1;   // 1: use the ping-pong kernels for Nq >= 256
-static int g_attn_ptmem = 1;  // 1: P-in-TMEM variant (attn5.cu) of the packed-half kernel
+int attn6_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
+                 const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
+                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, int q_tiles, cudaStream_t stream);
+static int g_attn_qtiles = 0;  // attn6: query tiles per CTA (0 = by K/V length, 1, 2)
+void set_attn_qtiles(int n) { g_attn_qtiles = n; }
+static int g_attn_ptmem = 2;  // 2: decoupled P-in-TMEM kernel (attn6.cu); 1: attn5.cu (P aliased onto S); 0: P through smem
 void set_attn_ptmem(int on) { g_attn_ptmem = on; }
 static int g_attn_w16 = 1;  // 1: 16-softmax-warp variant (attn4.cu) of the packed-half kernel
 void set_attn_w16(int on) { g_attn_w16 = on; }
@@ -330,6 +335,11 @@ int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long
     if (int e = encode_tokens(&tmV1, v1, ldkv1, H * 64, N1, B1)) return e;
   }
   if (g_attn_v2 && Nq >= 256) {
+    if (g_attn_ptmem == 2)
+      return attn6_launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
+                          has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,
+                          has1 ? static_cast<const int*>(kv1_base) : nullptr, scale * 1.4426950408889634f, accumulate,
+                          g_attn_qtiles, stream);
     auto launch = g_attn_h2 ? (g_attn_ptmem ? attn5_launch : (g_attn_w16 ? attn4_launch : attn3_launch)) : attn2_launch;
     return launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
                         has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,

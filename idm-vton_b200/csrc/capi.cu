@@ -32,6 +32,7 @@ void set_attn_v2(int on);
 void set_attn_h2(int on);
 void set_attn_w16(int on);
 void set_attn_ptmem(int on);
+void set_attn_qtiles(int n);
 int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const void* latents, const void* noise,
                   const void* coef, int do_cfg, void* out, cudaStream_t stream);
 }  // namespace vton
@@ -46,6 +47,10 @@ long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_2cta_auto") == 0) {
     vton::set_auto_v2(value);
+    return 0;
+  }
+  if (name && strcmp(name, "attention_q_tiles") == 0) {
+    vton::set_attn_qtiles(value);
     return 0;
   }
   if (name && strcmp(name, "attention_p_in_tmem") == 0) {

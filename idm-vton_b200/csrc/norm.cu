@@ -101,12 +101,28 @@ gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* partial, cons
   const int v = threadIdx.x % V;
   const int rl = threadIdx.x / V;
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  __shared__ double red_a[GN_THREADS / GN_GROUPS][GN_GROUPS], red_q[GN_THREADS / GN_GROUPS][GN_GROUPS];
+  {
+    // stage 2 of the statistics: 16 slices of the chunk list are summed in parallel (fixed order inside a slice, fixed
+    // order across slices), so the serial chain is gridDim.x/16 dependent L2 reads instead of gridDim.x
+    const int g = threadIdx.x & (GN_GROUPS - 1), sl = threadIdx.x / GN_GROUPS;
+    double a = 0.0, q = 0.0;
+    for (int ch = sl; ch < static_cast<int>(gridDim.x); ch += GN_THREADS / GN_GROUPS) {
+      const double2 pv = *reinterpret_cast<const double2*>(
+          partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + g) * 2);
+      a += pv.x;
+      q += pv.y;
+    }
+    red_a[sl][g] = a;
+    red_q[sl][g] = q;
+  }
+  __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
     double a = 0.0, q = 0.0;
-    for (int ch = 0; ch < static_cast<int>(gridDim.x); ++ch) {
-      const double* p = partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + threadIdx.x) * 2;
-      a += p[0];
-      q += p[1];
+#pragma unroll
+    for (int sl = 0; sl < GN_THREADS / GN_GROUPS; ++sl) {
+      a += red_a[sl][threadIdx.x];
+      q += red_q[sl][threadIdx.x];
     }
     const double n = static_cast<double>(cpg) * HW;
     const double mean = a / n;
@@ -180,6 +196,9 @@ int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAX_VEC = 8;  // per lane: up to 8 x 8 halves => C <= 2048
 
+// NV = ceil(C / 256) uint4 loads per lane, a compile-time bound so the row lives in 8*NV registers (C = 640: 24,
+// C = 1280: 40) and the SM holds enough warps to cover the load latency.
+template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* x, long long ldx, int rows, int C, const __half* gamma, const __half* beta, float eps,
                  __half* out, long long ldo) {
@@ -187,10 +206,10 @@ layernorm_kernel(const __half* x, long long ldx, int rows, int C, const __half* 
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
   const int V = C / 8;
-  float val[LN_MAX_VEC][8];
+  float val[NV][8];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < V) {
       const uint4 u = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
@@ -209,7 +228,7 @@ layernorm_kernel(const __half* x, long long ldx, int rows, int C, const __half* 
   const float mean = sum / C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < V) {
 #pragma unroll
@@ -223,7 +242,7 @@ layernorm_kernel(const __half* x, long long ldx, int rows, int C, const __half* 
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / C + eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < V) {
       const uint4 g = gamma ? *reinterpret_cast<const uint4*>(gamma + v * 8) : make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
@@ -248,9 +267,19 @@ int layernorm_impl(const void* x, long long ldx, int rows, int C, const void* ga
                    void* out, long long ldo, cudaStream_t stream) {
   VTON_CHECK_ARG(rows > 0 && C > 0, "layernorm: empty input");
   VTON_CHECK_ARG(C % 8 == 0 && C <= LN_MAX_VEC * 256 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: C=%d unsupported", C);
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(static_cast<const __half*>(x), ldx, rows, C,
-                                                     static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                                                     eps, static_cast<__half*>(out), ldo);
+  const int nv = cdiv(C / 8, 32);
+  auto go = [&](auto kern) {
+    kern<<<cdiv(rows, 8), 256, 0, stream>>>(static_cast<const __half*>(x), ldx, rows, C, static_cast<const __half*>(gamma),
+                                            static_cast<const __half*>(beta), eps, static_cast<__half*>(out), ldo);
+  };
+  switch (nv) {
+    case 1: go(layernorm_kernel<1>); break;
+    case 2: go(layernorm_kernel<2>); break;
+    case 3: go(layernorm_kernel<3>); break;
+    case 4: go(layernorm_kernel<4>); break;
+    case 5: go(layernorm_kernel<5>); break;
+    default: go(layernorm_kernel<LN_MAX_VEC>); break;
+  }
   count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;

@@ -58,6 +58,8 @@ def load(build_if_missing=True):
     lib.b200vton_set_option.restype = _i
     if os.environ.get("B200VTON_GEMM2", "1") == "0":
         lib.b200vton_set_option(b"gemm_2cta_auto", 0)
+    if os.environ.get("B200VTON_ATTN6", "1") == "0":
+        lib.b200vton_set_option(b"attention_p_in_tmem", 1)
     if os.environ.get("B200VTON_ATTN5", "1") == "0":
         lib.b200vton_set_option(b"attention_p_in_tmem", 0)
     if os.environ.get("B200VTON_ATTN4", "1") == "0":

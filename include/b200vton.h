@@ -32,7 +32,9 @@ long long b200vton_launch_count(void);
  * b200vton_attention on the two-tile ping-pong kernel when Nq >= 256; 0 keeps the one-tile kernel.
  * "attention_fp16_exp" = 1 (default) selects the ping-pong variant whose softmax evaluates exp2 two elements per SFU
  * op on fp16 arguments and lets the tensor core accumulate the row sums; 0 selects the fp32-softmax variant.
- * "attention_p_in_tmem" = 1 (default) keeps P in tensor memory (A operand of the P.V MMA from TMEM); with 0,
+ * "attention_p_in_tmem" = 2 (default) selects the decoupled P-in-TMEM kernel (fp32 softmax, S issued one tile ahead);
+ * ("attention_q_tiles" = 1 | 2 pins its query tiles per CTA, 0 = chosen from the K/V length);
+ * 1 the packed-half kernel with P aliased onto its S columns; with 0,
  * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one. */
 int b200vton_set_option(const char* name, int value);
 

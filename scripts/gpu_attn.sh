@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 date > gpurun_out/attn.log
-( timeout 420 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attention" --timeout 200 -p no:cacheprovider -x -s >> gpurun_out/attn.log 2>&1; echo "attention tests exit $?" | tee -a gpurun_out/attn.log; tail -n 8 gpurun_out/attn.log )
+( timeout 420 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "attention or groupnorm or layernorm" --timeout 200 -p no:cacheprovider -x -s >> gpurun_out/attn.log 2>&1; echo "attention tests exit $?" | tee -a gpurun_out/attn.log; tail -n 8 gpurun_out/attn.log )
 ( timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/attn_timing.log | tail -n 12
 import os, sys, json, torch
 sys.path.insert(0, ".")
@@ -15,12 +15,26 @@ for (B, H, N, Ng, tag) in [(4, 10, 3072, 3072, "L1 self+garment"), (4, 20, 768, 
     gv = rnd(max(B // 2, 1), Ng, C) if Ng else None
     fl = 4.0 * B * H * N * N * 64 + (4.0 * (B // 2) * H * N * Ng * 64 if Ng else 0)
     res = {}
-    for name, opts in (("attn5_ptmem", {"attention_p_in_tmem": 1, "attention_fp16_exp": 1}), ("attn4_16warps", {"attention_p_in_tmem": 0, "attention_16_warps": 1, "attention_fp16_exp": 1}), ("attn3_8warps", {"attention_16_warps": 0, "attention_fp16_exp": 1}), ("attn2_fp32", {"attention_fp16_exp": 0})):
+    for name, opts in (("attn6_q1", {"attention_p_in_tmem": 2, "attention_q_tiles": 1}), ("attn6_q2", {"attention_p_in_tmem": 2, "attention_q_tiles": 2}), ("attn5_ptmem", {"attention_p_in_tmem": 1, "attention_fp16_exp": 1})):
         for kk, vv in opts.items():
             L.set_option(kk, vv)
         ms = timeit(lambda: L.attention(q, k, v, gk, gv, kv1_off=B // 2, heads=H))
         res[name] = round(fl / ms / 1e9, 1)
-    L.set_option("attention_16_warps", 1); L.set_option("attention_fp16_exp", 1); L.set_option("attention_p_in_tmem", 1)
+    L.set_option("attention_16_warps", 1); L.set_option("attention_fp16_exp", 1); L.set_option("attention_p_in_tmem", 2); L.set_option("attention_q_tiles", 0)
     print(json.dumps({"tag": tag, "tflops": res}))
+PY
+)
+( timeout 200 python - <<'PY' 2>&1 | tee gpurun_out/norm_timing.log | tail -n 6
+import sys, json, torch
+sys.path.insert(0, ".")
+from idm_vton_b200 import lib as L
+from scripts.microbench import timeit, rnd
+L.load()
+for (B, HW, C) in [(4, 3072, 640), (4, 768, 1280), (4, 12288, 320)]:
+    xs, g, be = rnd(B, HW, C), rnd(C), rnd(C)
+    gn = timeit(lambda: L.groupnorm(xs, g, be, 1e-5, True))
+    ln = timeit(lambda: L.layernorm(xs.view(-1, C), g, be))
+    mb = 2 * xs.numel() * 2 / 1e6
+    print(json.dumps({"shape": [B, HW, C], "gn_us": round(gn * 1e3, 1), "gn_GBps": round(1.5 * mb / gn, 0), "ln_us": round(ln * 1e3, 1), "ln_GBps": round(mb / ln, 0)}))
 PY
 )

@@ -404,12 +404,14 @@ def test_attention_fp16_exp_vs_fp32_softmax(lib):
     for qscale in (1.0, 4.0):
         q, k, v = rnd(B, N, C, scale=qscale, seed=1), rnd(B, N, C, seed=2), rnd(B, N, C, seed=3)
         ref = _attn_ref(q, k, v, H, 0.125)
-        o3 = lib.attention(q, k, v, heads=H)
-        lib.set_option("attention_fp16_exp", 0)
+        lib.set_option("attention_p_in_tmem", 0)
         try:
+            o3 = lib.attention(q, k, v, heads=H)
+            lib.set_option("attention_fp16_exp", 0)
             o2 = lib.attention(q, k, v, heads=H)
         finally:
             lib.set_option("attention_fp16_exp", 1)
+            lib.set_option("attention_p_in_tmem", 2)
         e3, e2 = close(o3, ref, tol=4e-3), close(o2, ref, tol=4e-3)
         print(f"qscale {qscale}: fp16-exp err {e3:.2e}, fp32-softmax err {e2:.2e}")
 
@@ -428,33 +430,48 @@ def test_attention_16_warp_variant_matches_8_warp(lib):
         o8 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
     finally:
         lib.set_option("attention_16_warps", 1)
-        lib.set_option("attention_p_in_tmem", 1)
+        lib.set_option("attention_p_in_tmem", 2)
     ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
     close(o16[Bp:], ref_c, tol=3e-3)
     close(o16, o8, tol=2e-3)
 
 
 def test_attention_p_in_tmem_variant(lib):
-    """attn5.cu (P kept in tensor memory, TS-form P.V MMA) vs attn3.cu (P through shared memory) and the fp32 reference:
-    two segments with ragged tails, the zero-KV half, the accumulate mode and a peaky distribution."""
+    """attn6.cu (default: P in its own tensor-memory columns, S issued one tile ahead, fp32 softmax) and attn5.cu (P
+    aliased onto S, packed-half softmax) vs attn3.cu (P through shared memory) and the fp32 reference: two segments
+    with ragged tails, the zero-KV half, the accumulate mode and a peaky distribution."""
     Bp, H, N, Ng = 2, 5, 640, 1000
     C = H * 64
     qkv = rnd(2 * Bp, N, 3 * C, seed=21)
     q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
     gkv = rnd(Bp, Ng, 2 * C, seed=22)
     o5 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
-    lib.set_option("attention_p_in_tmem", 0)
-    lib.set_option("attention_16_warps", 0)
     try:
+        lib.set_option("attention_p_in_tmem", 1)
+        o5b = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+        lib.set_option("attention_p_in_tmem", 0)
+        lib.set_option("attention_16_warps", 0)
         o3 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
     finally:
         lib.set_option("attention_16_warps", 1)
-        lib.set_option("attention_p_in_tmem", 1)
+        lib.set_option("attention_p_in_tmem", 2)
+    close(o5b, o3, tol=2e-3)
     ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
     ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
     close(o5[Bp:], ref_c, tol=3e-3)
     close(o5[:Bp], ref_u, tol=3e-3)
     close(o5, o3, tol=2e-3)
+    for qt in (1, 2):   # one query tile per CTA (two CTAs per SM) / two query tiles sharing each K/V tile
+        lib.set_option("attention_q_tiles", qt)
+        try:
+            oq = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
+            q9, k9, v9 = rnd(1, 2048, 128, scale=4.0, seed=33), rnd(1, 2048, 128, seed=34), rnd(1, 2048, 128, seed=35)
+            o9 = lib.attention(q9, k9, v9, heads=2)
+        finally:
+            lib.set_option("attention_q_tiles", 0)
+        close(oq[Bp:], ref_c, tol=3e-3)
+        close(oq[:Bp], ref_u, tol=3e-3)
+        close(o9, _attn_ref(q9, k9, v9, 2, 0.125), tol=4e-3)
     # peaky scores exercise the lazy rescale of O in tensor memory; long single segment exercises the stage ring wrap
     q2, k2, v2 = rnd(1, 2048, 128, scale=4.0, seed=23), rnd(1, 2048, 128, seed=24), rnd(1, 2048, 128, seed=25)
     close(lib.attention(q2, k2, v2, heads=2), _attn_ref(q2, k2, v2, 2, 0.125), tol=4e-3)
