@@ -138,6 +138,8 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();   // set-up above overlapped the previous kernel's tail; Q/K/V are visible from here
 
   if (warp == 0) {
     // ===================== TMA producer: Q, then K(0) | K(1) V(0) | K(2) V(1) | ... (consumption order) =====
@@ -399,10 +401,12 @@ int attn6_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensor
   if (q_tiles == 0) q_tiles = 1;
   if (q_tiles == 1) {
     dim3 grid((Nq + 127) / 128, H, B);
-    attn6_kernel<1><<<grid, A6Cfg<1>::THREADS, A6Cfg<1>::SMEM_TOTAL, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+    VTON_CUDA(launch_kernel(attn6_kernel<1>, grid, dim3(A6Cfg<1>::THREADS), A6Cfg<1>::SMEM_TOTAL, stream, tmQ, tmK0, tmV0,
+                            tmK1, tmV1, p));
   } else {
     dim3 grid((Nq + 255) / 256, H, B);
-    attn6_kernel<2><<<grid, A6Cfg<2>::THREADS, A6Cfg<2>::SMEM_TOTAL, stream>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+    VTON_CUDA(launch_kernel(attn6_kernel<2>, grid, dim3(A6Cfg<2>::THREADS), A6Cfg<2>::SMEM_TOTAL, stream, tmQ, tmK0, tmV0,
+                            tmK1, tmV1, p));
   }
   count_launch();
   VTON_CUDA(cudaGetLastError());

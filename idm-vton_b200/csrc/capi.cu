@@ -11,6 +11,9 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
                  const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
                  cudaStream_t stream);
+int cross_attn_impl(const void* q, long long ldq, const void* kt, const void* vt, long long ldkv_t, int Nt,
+                    const void* ki, const void* vi, long long ldkv_i, int Ni, void* out, long long ldo, int B, int H,
+                    int Nq, float scale, float ip_scale, cudaStream_t stream);
 int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long long ldkv0, const void* k1,
               const void* v1, long long ldkv1, void* out, long long ldo, int B, int H, int Nq, int N0, int N1, int B1,
               int kv1_off, int kv1_mod, const void* kv1_base, float scale, int accumulate, cudaStream_t stream);
@@ -47,6 +50,10 @@ long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_2cta_auto") == 0) {
     vton::set_auto_v2(value);
+    return 0;
+  }
+  if (name && strcmp(name, "programmatic_launch") == 0) {
+    vton::set_pdl(value);
     return 0;
   }
   if (name && strcmp(name, "attention_q_tiles") == 0) {
@@ -94,6 +101,13 @@ int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v
                        void* stream) {
   return vton::attn_impl(q, ldq, k0, v0, ldkv0, k1, v1, ldkv1, out, ldo, B, H, Nq, N0, N1, B1, kv1_off, kv1_mod, kv1_base, scale,
                          accumulate, S(stream));
+}
+
+int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const void* vt, int64_t ldkv_t, int Nt,
+                             const void* ki, const void* vi, int64_t ldkv_i, int Ni, void* out, int64_t ldo, int B,
+                             int H, int Nq, float scale, float ip_scale, void* stream) {
+  return vton::cross_attn_impl(q, ldq, kt, vt, ldkv_t, Nt, ki, vi, ldkv_i, Ni, out, ldo, B, H, Nq, scale, ip_scale,
+                               S(stream));
 }
 
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,

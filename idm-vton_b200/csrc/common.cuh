@@ -198,6 +198,11 @@ __device__ __forceinline__ void tc_mma_f16_2cta(uint32_t d_tmem, uint64_t a_desc
       : "memory");
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start its set-up now / wait until every kernel
+// this one depends on has completed and its memory is visible (no-ops when launched without the attribute).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor bit layout): fp16 A/B, fp32 D, K-major A,
 // B K-major (b_mn_major = 0) or MN-major (1).
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t b_mn_major) {

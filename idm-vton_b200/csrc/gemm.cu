@@ -79,6 +79,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();   // set-up above overlapped the previous kernel's tail; its results are visible from here
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -169,9 +171,8 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     VTON_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmS0, tmS1, tmBs, p);
+  VTON_CUDA(launch_kernel(kern, dim3(grid), dim3(192), L::TOTAL, stream, tmA, tmB, tmS0, tmS1, tmBs, p));
   count_launch();
-  VTON_CUDA(cudaGetLastError());
   return kOk;
 }
 

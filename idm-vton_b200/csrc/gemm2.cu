@@ -72,6 +72,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit / TMA
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();            // everything above overlapped the previous kernel's tail; its results are visible from here
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
@@ -231,13 +233,15 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VTON_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p, m_pairs));
   count_launch();
   return kOk;

@@ -18,6 +18,9 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return g_err; }
 
+static std::atomic<int> g_pdl{1};
+int pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }

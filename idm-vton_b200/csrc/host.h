@@ -40,6 +40,30 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (option "programmatic_launch", default on): the hot kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, call griddepcontrol.launch_dependents on entry and
+// griddepcontrol.wait after their own set-up (barrier init, TMEM allocation, tensor-map prefetch) and before they
+// touch any global memory, so the set-up of kernel n+1 and the launch latency overlap the tail of kernel n — inside
+// the captured denoise step (~930 launches) that is the gap between every pair of kernels.
+int pdl_enabled();
+void set_pdl(int on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Number of kernels this library has launched (or recorded into a capturing stream) since load.
 void count_launch(int n = 1);
 long long launch_count();

@@ -32,6 +32,8 @@ __device__ __forceinline__ uint4 gn_load(const GnSrc& s, long long row, int v) {
 //   stage 1: CTA (chunk, b) reduces its rows -> partial[b][chunk][g] = {sum, sum of squares} (fixed reduction order)
 //   stage 2: the apply kernel's first 32 threads sum the chunk partials of their group in order (double).
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int rows_per_cta, double* partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = src.C0 + src.C1;
   const int V = C / 8;
   const int cpg = C / GN_GROUPS;
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* partial, const __half* gamma, const __half* beta,
                 float eps, int silu, __half* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = src.C0 + src.C1;
   const int V = C / 8;
   const int cpg = C / GN_GROUPS;
@@ -182,12 +186,12 @@ int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW
   const int rows_per_cta = cdiv(HW, chunks);
   chunks = cdiv(HW, rows_per_cta);
   dim3 grid(chunks, B);
-  gn_stats_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<double*>(stats_ws));
-  gn_apply_kernel<<<grid, GN_THREADS, 0, stream>>>(src, HW, rows_per_cta, static_cast<const double*>(stats_ws),
-                                                   static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                                                   eps, silu, static_cast<__half*>(out));
+  VTON_CUDA(launch_kernel(gn_stats_kernel, grid, dim3(GN_THREADS), 0, stream, src, HW, rows_per_cta,
+                          static_cast<double*>(stats_ws)));
+  VTON_CUDA(launch_kernel(gn_apply_kernel, grid, dim3(GN_THREADS), 0, stream, src, HW, rows_per_cta,
+                          static_cast<const double*>(stats_ws), static_cast<const __half*>(gamma),
+                          static_cast<const __half*>(beta), eps, silu, static_cast<__half*>(out)));
   count_launch(2);
-  VTON_CUDA(cudaGetLastError());
   return kOk;
 }
 
@@ -202,6 +206,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* x, long long ldx, int rows, int C, const __half* gamma, const __half* beta, float eps,
                  __half* out, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -269,19 +275,21 @@ int layernorm_impl(const void* x, long long ldx, int rows, int C, const void* ga
   VTON_CHECK_ARG(C % 8 == 0 && C <= LN_MAX_VEC * 256 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm: C=%d unsupported", C);
   const int nv = cdiv(C / 8, 32);
   auto go = [&](auto kern) {
-    kern<<<cdiv(rows, 8), 256, 0, stream>>>(static_cast<const __half*>(x), ldx, rows, C, static_cast<const __half*>(gamma),
-                                            static_cast<const __half*>(beta), eps, static_cast<__half*>(out), ldo);
+    return launch_kernel(kern, dim3(cdiv(rows, 8)), dim3(256), 0, stream, static_cast<const __half*>(x), ldx, rows, C,
+                         static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps,
+                         static_cast<__half*>(out), ldo);
   };
+  cudaError_t le = cudaSuccess;
   switch (nv) {
-    case 1: go(layernorm_kernel<1>); break;
-    case 2: go(layernorm_kernel<2>); break;
-    case 3: go(layernorm_kernel<3>); break;
-    case 4: go(layernorm_kernel<4>); break;
-    case 5: go(layernorm_kernel<5>); break;
-    default: go(layernorm_kernel<LN_MAX_VEC>); break;
+    case 1: le = go(layernorm_kernel<1>); break;
+    case 2: le = go(layernorm_kernel<2>); break;
+    case 3: le = go(layernorm_kernel<3>); break;
+    case 4: le = go(layernorm_kernel<4>); break;
+    case 5: le = go(layernorm_kernel<5>); break;
+    default: le = go(layernorm_kernel<LN_MAX_VEC>); break;
   }
+  VTON_CUDA(le);
   count_launch();
-  VTON_CUDA(cudaGetLastError());
   return kOk;
 }
 

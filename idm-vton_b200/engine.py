@@ -319,9 +319,14 @@ class UNetEngine:
         n2 = L.layernorm(h, blk.ln2w, blk.ln2b)
         q2 = L.gemm(n2, blk.wq2).view(B, N, C)
         kv_t, kv_i = ctx
-        a2 = L.attention(q2, kv_t[..., :C], kv_t[..., C:], heads=H)
-        if kv_i is not None:
-            L.attention(q2, kv_i[..., :C], kv_i[..., C:], heads=H, accumulate=True, out=a2)
+        if kv_t.shape[1] <= 80 and (kv_i is None or kv_i.shape[1] <= 16):
+            # text + image-token cross-attention fused in one launch (both key sets fit one score tile)
+            a2 = L.cross_attention(q2, kv_t[..., :C], kv_t[..., C:], None if kv_i is None else kv_i[..., :C],
+                                   None if kv_i is None else kv_i[..., C:], heads=H)
+        else:
+            a2 = L.attention(q2, kv_t[..., :C], kv_t[..., C:], heads=H)
+            if kv_i is not None:
+                L.attention(q2, kv_i[..., :C], kv_i[..., C:], heads=H, accumulate=True, out=a2)
         h = L.gemm(a2.view(B * N, C), blk.wo2, bias=blk.bo2, residual=h)
         n3 = L.layernorm(h, blk.ln3w, blk.ln3b)
         ff = L.gemm(n3, blk.wff1, bias=blk.bff1, geglu=True,

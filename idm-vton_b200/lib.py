@@ -21,6 +21,7 @@ SIGNATURES = {
                               _vp, _i64, _i, _vp],
     "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i,
                            _vp],
+    "b200vton_cross_attention": [_vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _f, _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
     "b200vton_nchw_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -58,6 +59,8 @@ def load(build_if_missing=True):
     lib.b200vton_set_option.restype = _i
     if os.environ.get("B200VTON_GEMM2", "1") == "0":
         lib.b200vton_set_option(b"gemm_2cta_auto", 0)
+    if os.environ.get("B200VTON_PDL", "1") == "0":
+        lib.b200vton_set_option(b"programmatic_launch", 0)
     if os.environ.get("B200VTON_ATTN6", "1") == "0":
         lib.b200vton_set_option(b"attention_p_in_tmem", 1)
     if os.environ.get("B200VTON_ATTN5", "1") == "0":
@@ -174,6 +177,30 @@ def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=No
                                 out.stride(1), B, H, Nq, N0, n1, B1, kv1_off, kv1_mod, _p(kv1_base), float(scale),
                                 int(accumulate), _stream())
     _check(rc, "b200vton_attention")
+    return out
+
+
+def cross_attention(q, kt, vt, ki=None, vi=None, heads=None, scale=None, ip_scale=1.0, out=None):
+    """Text (+ IP-Adapter image token) cross-attention in one launch. q: [B,Nq,*]; kt/vt: [B,Nt<=80,*]; ki/vi:
+    [B,Ni<=16,*] or None. 3-D views with contiguous last dim (slices of fused [K|V] buffers are fine)."""
+    lib = load()
+    B, Nq = q.shape[0], q.shape[1]
+    H = heads
+    Nt = kt.shape[1]
+    assert q.stride(2) == 1 and kt.stride(2) == 1 and vt.stride() == kt.stride() and kt.shape[0] == B
+    assert q.stride(0) == Nq * q.stride(1) and kt.stride(0) == Nt * kt.stride(1)
+    if scale is None:
+        scale = 64 ** -0.5
+    if out is None:
+        out = torch.empty(B, Nq, H * 64, dtype=torch.float16, device=q.device)
+    assert out.stride(2) == 1 and out.stride(0) == Nq * out.stride(1)
+    Ni, ldi = 0, 0
+    if ki is not None:
+        Ni, ldi = ki.shape[1], ki.stride(1)
+        assert ki.stride(2) == 1 and vi.stride() == ki.stride() and ki.shape[0] == B and ki.stride(0) == Ni * ldi
+    rc = lib.b200vton_cross_attention(_p(q), q.stride(1), _p(kt), _p(vt), kt.stride(1), Nt, _p(ki), _p(vi), ldi, Ni,
+                                      _p(out), out.stride(1), B, H, Nq, float(scale), float(ip_scale), _stream())
+    _check(rc, "b200vton_cross_attention")
     return out
 
 

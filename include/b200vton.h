@@ -35,7 +35,9 @@ long long b200vton_launch_count(void);
  * "attention_p_in_tmem" = 2 (default) selects the decoupled P-in-TMEM kernel (fp32 softmax, S issued one tile ahead);
  * ("attention_q_tiles" = 1 | 2 pins its query tiles per CTA, 0 = chosen from the K/V length);
  * 1 the packed-half kernel with P aliased onto its S columns; with 0,
- * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one. */
+ * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one.
+ * "programmatic_launch" = 1 (default) launches the hot kernels with programmatic stream serialization (their set-up
+ * overlaps the previous kernel's tail; they wait for it before touching memory); 0 = plain stream order. */
 int b200vton_set_option(const char* name, int value);
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear on the hot path — attn to_q/to_k/to_v/to_out
@@ -76,6 +78,18 @@ int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v
                        const void* v1, int64_t ldkv1, void* out, int64_t ldo, int B, int H, int Nq, int N0, int N1,
                        int B1, int kv1_off, int kv1_mod, const void* kv1_base, float scale, int accumulate,
                        void* stream);
+
+/* Decoupled cross-attention (attn2 of every transformer block) in one launch:
+ *   out = fp16( fp16(softmax(Q Kt^T * scale) Vt) + fp16(ip_scale * fp16(softmax(Q Ki^T * scale) Vi)) ),  head_dim 64,
+ * Kt/Vt = [B, Nt <= 80, *] the text tokens (attn2.to_k / to_v), Ki/Vi = [B, Ni <= 16, *] the IP-Adapter image tokens
+ * (processor to_k_ip / to_v_ip); Ni = 0 (ki = vi = NULL) is the plain text cross-attention of the garment UNet.
+ * Replaces IPAttnProcessor2_0.__call__ (ip_adapter/attention_processor.py: two scaled_dot_product_attention calls and
+ * hidden_states + self.scale * ip_hidden_states), called as attn2 at src/attentionhacked_tryon.py:368-380, and
+ * AttnProcessor2_0 at src/attentionhacked_garmnet.py:371-383. Same result as two b200vton_attention calls
+ * (the second with accumulate = 1), one kernel instead of two. Layouts as b200vton_attention. */
+int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const void* vt, int64_t ldkv_t, int Nt,
+                             const void* ki, const void* vi, int64_t ldkv_i, int Ni, void* out, int64_t ldo, int B,
+                             int H, int Nq, float scale, float ip_scale, void* stream);
 
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
  * fp32 statistics (deterministic two-stage reduction, no atomics), optional SiLU, fp16 out [B*HW, C0+C1].

@@ -16,6 +16,8 @@ for (B, H, N, tag) in [(4, 20, 768, "L2"), (4, 10, 3072, "L1")]:
     out = torch.empty_like(q)
     t_text = timeit(lambda: L.attention(q, kt, vt, heads=H, out=out))
     t_ip = timeit(lambda: L.attention(q, ki, vi, heads=H, out=out, accumulate=True))
-    print(json.dumps({"tag": tag, "text_us": round(t_text * 1e3, 1), "ip_us": round(t_ip * 1e3, 1)}))
+    t_f = timeit(lambda: L.cross_attention(q, kt, vt, ki, vi, heads=H, out=out))
+    t_t = timeit(lambda: L.cross_attention(q, kt, vt, heads=H, out=out))
+    print(json.dumps({"tag": tag, "text_us": round(t_text * 1e3, 1), "ip_us": round(t_ip * 1e3, 1), "fused_us": round(t_f * 1e3, 1), "fused_text_only_us": round(t_t * 1e3, 1)}))
 PY
 )

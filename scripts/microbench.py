@@ -32,6 +32,32 @@ def timeit(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
+def timeit_graph(fn, n=20, reps=5):
+    """Per-launch GPU time of fn inside a replayed CUDA graph of n back-to-back launches (no host time, L2-warm data —
+    how the kernel runs inside the captured denoise step)."""
+    fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        fn()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(n):
+                fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        g.replay()
+        e_.record()
+        torch.cuda.synchronize()
+        ts.append(s_.elapsed_time(e_) / n)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def rnd(*s, scale=1.0):
     return (torch.randn(*s, device=dev) * scale).half()
 

@@ -481,3 +481,36 @@ def test_attention_p_in_tmem_variant(lib):
     acc = base.clone()
     lib.attention(q2, k3, v3, heads=2, out=acc, accumulate=True)
     close(acc, base.float() + _attn_ref(q2, k3, v3, 2, 0.125), tol=4e-3)
+
+
+@pytest.mark.parametrize("B,H,N,Nt,Ni", [(2, 10, 256, 77, 16), (4, 20, 768, 77, 16), (2, 10, 3072, 77, 0),
+                                         (1, 5, 200, 77, 16), (3, 2, 40, 33, 7), (2, 4, 128, 80, 16)])
+def test_cross_attention_fused(lib, B, H, N, Nt, Ni):
+    """attn_cross.cu: text + IP-token cross-attention in one launch vs the fp32 reference with the reference's fp16
+    rounding points (two softmaxes, fp16 outputs summed in fp16) and vs the two-launch accumulate path."""
+    C = H * 64
+    q = rnd(B, N, 3 * C, seed=1)[..., C:2 * C]              # strided view, like a slice of a fused projection
+    kvt = rnd(B, Nt, 2 * C, seed=2)
+    kt, vt = kvt[..., :C], kvt[..., C:]
+    ref = r16(_attn_ref(q, kt, vt, H, 0.125))
+    ki = vi = None
+    if Ni:
+        kvi = rnd(B, Ni, 2 * C, seed=3)
+        ki, vi = kvi[..., :C], kvi[..., C:]
+        ref = r16(ref + r16(_attn_ref(q, ki, vi, H, 0.125)))
+    out = lib.cross_attention(q, kt, vt, ki, vi, heads=H)
+    close(out, ref, tol=3e-3)
+    two = lib.attention(q, kt, vt, heads=H)
+    if Ni:
+        two = lib.attention(q, ki, vi, heads=H, accumulate=True, out=two)
+    close(out, two, tol=2e-3)
+
+
+def test_cross_attention_ip_scale_and_peaky(lib):
+    B, H, N = 2, 4, 384
+    C = H * 64
+    q = rnd(B, N, C, scale=4.0, seed=5)
+    kt, vt, ki, vi = rnd(B, 77, C, seed=6), rnd(B, 77, C, seed=7), rnd(B, 16, C, seed=8), rnd(B, 16, C, seed=9)
+    out = lib.cross_attention(q, kt, vt, ki, vi, heads=H, ip_scale=0.5)
+    ref = r16(r16(_attn_ref(q, kt, vt, H, 0.125)) + r16(0.5 * r16(_attn_ref(q, ki, vi, H, 0.125))))
+    close(out, ref, tol=3e-3)
