@@ -174,6 +174,31 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         b0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.bb;
       }
       const int out_n0 = n_tile * OUT_COLS;
+      // The residual rows do not depend on the accumulator: fetch the first chunk's segment before waiting for the
+      // main loop and every later one a chunk ahead, so their L2 latency never sits on the epilogue's critical path
+      // (it was 45% of the epilogue's stall samples and doubled the time of the short-K out-projections).
+      constexpr bool PRE_RES = ((EPI & EPI_RES) != 0) && ((EPI & EPI_RUNTIME) == 0) && !GEGLU;
+      uint4 rcur[4], rnxt[4];
+      auto res_fetch = [&](int c, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ncol = out_n0 + c * 32 + g * 8;
+          dst[g] = (c < NCHUNK && out_row >= 0 && ncol < p.N)
+                       ? __ldg(reinterpret_cast<const uint4*>(p.residual + out_row * p.ld_res + ncol))
+                       : make_uint4(0, 0, 0, 0);
+        }
+      };
+      constexpr bool PRE_BIAS = ((EPI & EPI_BIAS) != 0) && ((EPI & EPI_RUNTIME) == 0) && !GEGLU;
+      uint4 bcur[4], bnxt[4];
+      auto bias_fetch = [&](int c, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ncol = out_n0 + c * 32 + g * 8;
+          dst[g] = (c < NCHUNK && ncol < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.bias + ncol)) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (PRE_RES) res_fetch(half, rcur);
+      if (PRE_BIAS) bias_fetch(half, bcur);
       if (lane == 0) tma_store_wait_read<0>();   // this warp's stores of the previous tile have drained the ring
       __syncwarp();
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -182,7 +207,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
         uint32_t pk[16];
-        epilogue_chunk<BN, GEGLU, EPI>(p, t_row, 0, n_tile, out_row, sample, c, pk);
+        if (PRE_RES) res_fetch(c + 2, rnxt);
+        if (PRE_BIAS) bias_fetch(c + 2, bnxt);
+        epilogue_chunk<BN, GEGLU, EPI>(p, t_row, 0, n_tile, out_row, sample, c, pk, PRE_RES ? rcur : nullptr,
+                                       PRE_BIAS ? bcur : nullptr);
+        if (PRE_RES) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rcur[g] = rnxt[g];
+        }
+        if (PRE_BIAS) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bcur[g] = bnxt[g];
+        }
         const uint32_t slot = (c >> 1) * 2048;
         uint8_t* dst = my_stage_gen + slot + lane * 64;
 #pragma unroll

@@ -99,6 +99,24 @@ __device__ __forceinline__ void add_h8(float (&v)[8], const __half* src) {
     v[2 * j + 1] += a.y;
   }
 }
+__device__ __forceinline__ void add_u4(float (&v)[8], const uint4 u) {   // v += u (8 halves)
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_h2(w[j]);
+    v[2 * j] += a.x;
+    v[2 * j + 1] += a.y;
+  }
+}
+__device__ __forceinline__ void round_add_u4(float (&v)[8], const uint4 u) {   // v = fp16(v) + u (8 halves)
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_h2(w[j]);
+    v[2 * j] = round_h(v[2 * j]) + a.x;
+    v[2 * j + 1] = round_h(v[2 * j + 1]) + a.y;
+  }
+}
 __device__ __forceinline__ void round_add_h8(float (&v)[8], const __half* src) {   // v = fp16(v) + src
   const uint4 u = *reinterpret_cast<const uint4*>(src);
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -115,7 +133,8 @@ __device__ __forceinline__ void round_add_h8(float (&v)[8], const __half* src) {
 // don't-care values (the sinks clip them).
 template <int BN, bool GEGLU, int EPI>
 __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, long long out_row, int sample, int c,
-                                              const uint32_t (&acc)[32], const uint32_t (&acc2)[32], uint32_t (&pk)[16]) {
+                                              const uint32_t (&acc)[32], const uint32_t (&acc2)[32], uint32_t (&pk)[16],
+                                              const uint4* res_pre = nullptr, const uint4* bias_pre = nullptr) {
   constexpr bool RT = (EPI & EPI_RUNTIME) != 0;
   const bool has_bias = RT ? (p.bias != nullptr) : ((EPI & EPI_BIAS) != 0);
   const bool has_rowvec = RT ? (p.rowvec != nullptr) : ((EPI & EPI_ROWVEC) != 0);
@@ -148,7 +167,11 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
         v[j] = hv * round_h(gelu_erf_fast(gv));  // fp16(h) * fp16(gelu(fp16(gate)))
       }
     } else {
-      if (has_bias && col_ok) add_h8(v, p.bias + ncol);
+      if (bias_pre != nullptr) {
+        if (has_bias) add_u4(v, bias_pre[g]);   // prefetched by the caller (zeros past N)
+      } else if (has_bias && col_ok) {
+        add_h8(v, p.bias + ncol);
+      }
       if (RT && p.act_gelu) {   // rare (Resampler FeedForward): keep it rolled
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(round_h(v[j]));
@@ -162,7 +185,11 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = round_h(s[j]) + round_h(v[j]);
       }
-      if (has_res && col_ok && res_row != nullptr) round_add_h8(v, res_row + ncol);
+      if (res_pre != nullptr) {   // residual row segment prefetched by the caller (zeros where it does not apply)
+        if (has_res) round_add_u4(v, res_pre[g]);
+      } else if (has_res && col_ok && res_row != nullptr) {
+        round_add_h8(v, res_row + ncol);
+      }
     }
     pk[g * 4 + 0] = pack_h2(v[0], v[1]);
     pk[g * 4 + 1] = pack_h2(v[2], v[3]);
@@ -173,12 +200,13 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
 
 template <int BN, bool GEGLU, int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t t_row, uint32_t sc_col_off, int n_tile,
-                                               long long out_row, int sample, int c, uint32_t (&pk)[16]) {
+                                               long long out_row, int sample, int c, uint32_t (&pk)[16],
+                                               const uint4* res_pre = nullptr, const uint4* bias_pre = nullptr) {
   uint32_t acc[32];
   uint32_t acc2[32];
   epilogue_load<BN, GEGLU, EPI>(p, t_row, sc_col_off, c, acc, acc2);
   tmem_ld_wait();
-  epilogue_math<BN, GEGLU, EPI>(p, n_tile, out_row, sample, c, acc, acc2, pk);
+  epilogue_math<BN, GEGLU, EPI>(p, n_tile, out_row, sample, c, acc, acc2, pk, res_pre, bias_pre);
 }
 
 // Sink 1 (1-CTA kernel): registers -> global, each thread writes its own row.
