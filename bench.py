@@ -90,8 +90,8 @@ def load_peaks():
 # DRAM traffic of one launch of the dominant kernel shape, from `ncu --set full` (dram__bytes_read.sum +
 # dram__bytes_write.sum; see profiles/r1_ncu_final_summary.json). Algorithmic bytes of that launch: A 7.9 MB + W 26.2 MB
 # + out 31.5 MB = 65.5 MB.
-DOMINANT_KERNEL_DRAM_BYTES = None
-DOMINANT_KERNEL_TRAFFIC_SOURCE = "profiles/r1_ncu_final_summary.json"
+DOMINANT_KERNEL_DRAM_BYTES = 36954112   # 34.14 MB read + 2.81 MB written: the 31.5 MB output stays in the 126 MB L2
+DOMINANT_KERNEL_TRAFFIC_SOURCE = "profiles/r1_ncu_v5_summary.json (ncu --set full, one launch after an L2 flush)"
 
 
 def time_dominant_kernel(device, batch, n=20):
@@ -544,6 +544,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true", help="run one denoise step inside a cudaProfiler range (ncu)")
     args = ap.parse_args()
+    # watchdog: a bench that is still running after 20 minutes is stuck (the default run takes ~3 min) — dump every
+    # Python stack to stderr and exit non-zero instead of occupying the GPU box until the caller's limit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("B200VTON_BENCH_WATCHDOG", "1200")), exit=True, file=sys.stderr)
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         run_reference(args, rank, int(os.environ.get("WORLD_SIZE", "1")))

@@ -167,6 +167,16 @@ __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same, multicast: the box lands at the same CTA-relative smem offset of every CTA in cta_mask (cluster ranks) and
+// the bytes are credited to the barrier of each destination CTA's pair leader.
+__device__ __forceinline__ void tma2_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                              int c3) {
   asm volatile(

@@ -177,12 +177,18 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int np = 1);
 
 // force_bn encoding: 0 = automatic kernel / tile choice; 64..256 = 1-CTA kernel (gemm.cu) with that tile width;
 // 1000 + {128,160,192,256} = 2-CTA persistent kernel (gemm2.cu) with that tile width.
 static int g_auto_v2 = 1;
 void set_auto_v2(int on) { g_auto_v2 = on; }
+// "gemm_cluster4": 1 lets large linear layers with 256-wide tiles run in four-CTA clusters that multicast the A slabs.
+// Measured SLOWER than two-CTA clusters at every config-2 shape (profiles/r1_gemm_cluster4.jsonl: 8192^3 1003 vs 1359
+// TFLOP/s, FF2 763 vs 1298) — four-CTA multicast does not lower the L2 output load on this part and the coupled
+// pairs lose slack — so it stays off; kept as a selectable variant (force_bn = 2256) with its parity test.
+static int g_cluster4 = 0;
+void set_cluster4(int on) { g_cluster4 = on; }
 
 static int pick_bn2(int N, bool geglu) {
   if (geglu) return N % 256 == 0 ? 256 : 128;
@@ -241,7 +247,13 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   VTON_CHECK_ARG(K % 64 == 0, "gemm: K=%d must be a multiple of 64", K);
   VTON_CHECK_ARG(N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "gemm: N/lda/ldw/ldo must be multiples of 8");
   VTON_CHECK_ARG(!geglu || (N % 16 == 0 && !residual && !rowvec), "gemm: bad GEGLU configuration");
+  int np = 1;
+  if (force_bn >= 2000) {   // 2000 + bn: the 2-CTA kernel in four-CTA clusters (A multicast)
+    np = 2;
+    force_bn -= 1000;
+  }
   const int bn2 = choose_v2(cdiv(M, BM), N, geglu != 0, false, force_bn);
+  if (force_bn == 0 && g_cluster4 && bn2 == 256 && cdiv(N, 256) >= 2 && M >= 1024 && K >= 512) np = 2;
   VTON_CHECK_ARG(bn2 == 0 || bn2 == 128 || bn2 == 160 || bn2 == 192 || bn2 == 256, "gemm: bad 2-CTA tile width %d", bn2);
   int bn = bn2 ? bn2 : pick_bn(N, force_bn);
   if (geglu && bn != 128 && bn != 256) bn = 128;
@@ -250,7 +262,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
-    uint32_t box[2] = {64, 128};
+    uint32_t box[2] = {64, static_cast<uint32_t>(np == 2 ? 64 : 128)};   // four-CTA clusters fetch A in 64-row halves
     if (int e = encode_tmap_f16(&tmA, A, 2, dims, strides, box)) return e;
   }
   {
@@ -272,7 +284,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   p.rows_per_sample = rows_per_sample;
   p.slabs_main = K / 64;
   p.act_gelu = (flags & 2) ? 1 : 0;
-  if (bn2) return gemm2_dispatch(bn, geglu != 0, tmA, tmB, p, cdiv(M, BM), stream);
+  if (bn2) return gemm2_dispatch(bn, geglu != 0, tmA, tmB, p, cdiv(M, BM), stream, np);
   return dispatch(bn, geglu != 0, tmA, tmB, tmA, tmA, tmB, p, cdiv(M, BM), stream);
 }
 

@@ -29,7 +29,12 @@ struct Smem2 {
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
-template <int BN, int STAGES, bool GEGLU, int EPI>
+// NP = MMA pairs per cluster. NP = 2 (linear layers only): a cluster of four CTAs owns two N-adjacent 256 x BN tiles
+// of the same 256 rows; CTA (pair, r) fetches one 64-row half of the pair-independent A slab r and multicasts it to
+// both pairs, so the L2 slices serve 24 KB instead of 32 KB per CTA and K slab — the chip-wide L2 output rate
+// (~6300 B/clk, 42 B/clk/SM) is what bounds these GEMMs at ~65% tensor-pipe utilisation, not the tensor cores.
+// A slot is recycled when BOTH pairs' MMAs have retired (empty barriers count NP multicast commits).
+template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1>
 __global__ void __launch_bounds__(320, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const GemmParams p, int m_pairs) {
@@ -47,10 +52,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int n_clusters = gridDim.x >> 1;
-  const int total_tiles = m_pairs * p.n_tiles;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;          // role inside the MMA pair (0 = leader)
+  const uint32_t pr = crank >> 1;           // pair inside the cluster (always 0 when NP == 1)
+  const int cluster_id = blockIdx.x / (2 * NP);
+  const int n_clusters = gridDim.x / (2 * NP);
+  const int n_super = (p.n_tiles + NP - 1) / NP;   // NP N-adjacent tiles per cluster step
+  const int total_tiles = m_pairs * n_super;
   const int slabs = p.slabs_main;
   constexpr uint32_t kTmemCols = 512;   // two accumulator stages of BN (<= 256) columns
 
@@ -60,7 +68,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), NP);   // one multicast commit per pair
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -81,8 +89,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters) {
-        const int n_tile = t % p.n_tiles;
-        const int m_tile = 2 * (t / p.n_tiles) + static_cast<int>(rank);
+        const int n_tile = (t % n_super) * NP + static_cast<int>(pr);
+        const int m_tile = 2 * (t / n_super) + static_cast<int>(rank);
         const int n0 = n_tile * BN + static_cast<int>(rank) * (BN / 2);
         int b0 = 0, y0 = 0, x0 = 0;
         if (p.conv) {
@@ -104,7 +112,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma2_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 + dx, y0 + dy, b0);
             tma2_load_2d(b_dst, &tmB, full_bar(stage), c0, tap * p.cout + n0);
           } else {
-            tma2_load_2d(a_dst, &tmA, full_bar(stage), s * BK, m_tile * BM);
+            if (NP == 2)   // my 64-row half of A slab `rank`, delivered to CTA (0, rank) and CTA (1, rank)
+              tma2_load_2d_mc(a_dst + pr * (A_BYTES / 2), &tmA, full_bar(stage), s * BK, m_tile * BM + pr * (BM / 2),
+                              static_cast<uint16_t>((1u << rank) | (1u << (2 + rank))));
+            else
+              tma2_load_2d(a_dst, &tmA, full_bar(stage), s * BK, m_tile * BM);
             tma2_load_2d(b_dst, &tmB, full_bar(stage), s * BK, n0);
           }
         }
@@ -135,9 +147,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint64_t b_desc = make_smem_desc_sw128(b_src + k * 32, 0, 1024);
             tc_mma_f16_2cta(d, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit_2cta(empty_bar(stage), 0x3);   // frees this smem slot in both CTAs
+          tc_commit_2cta(empty_bar(stage), NP == 2 ? 0xF : 0x3);   // this pair is done with the slot (all CTAs hear it)
         }
-        tc_commit_2cta(tfull_bar(acc), 0x3);        // accumulator stage complete, wake both epilogues
+        tc_commit_2cta(tfull_bar(acc), static_cast<uint16_t>(0x3u << (2 * pr)));   // wake this pair's epilogues
       }
     }
   } else {
@@ -162,8 +174,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
       const int acc = tile_iter & 1;
       const uint32_t acc_phase = (tile_iter >> 1) & 1;
-      const int n_tile = t % p.n_tiles;
-      const int m_tile = 2 * (t / p.n_tiles) + static_cast<int>(rank);
+      const int n_tile = (t % n_super) * NP + static_cast<int>(pr);
+      const int m_tile = 2 * (t / n_super) + static_cast<int>(rank);
       long long out_row;
       int sample;
       map_row(p, m_tile, row, &out_row, &sample);
@@ -236,7 +248,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);   // leader's barrier, one arrive per warp
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 2 * pr);   // pair leader's barrier, one arrive per warp
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -252,26 +264,45 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool GEGLU, int EPI>
+template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmParams& p,
                    int m_pairs, cudaStream_t stream) {
   using L = Smem2<BN, STAGES>;
-  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI>;
+  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI, NP>;
   static bool configured = false;
+  static int max_clusters = kSMs / (2 * NP);
   if (!configured) {
     VTON_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    if (NP > 1) {
+      // four-CTA clusters must sit inside one GPC: ask the driver how many fit on this part
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(kSMs / (2 * NP) * 2 * NP);
+      q.blockDim = dim3(320);
+      q.dynamicSmemBytes = L::TOTAL;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2 * NP;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      VTON_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+      VTON_CHECK_ARG(n > 0, "gemm2: no %d-CTA cluster fits on this device", 2 * NP);
+      if (n < max_clusters) max_clusters = n;
+    }
     configured = true;
   }
-  const int tiles = m_pairs * p.n_tiles;
-  const int clusters = tiles < kSMs / 2 ? tiles : kSMs / 2;
+  const int tiles = m_pairs * cdiv(p.n_tiles, NP);
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * clusters);
+  cfg.gridDim = dim3(2 * NP * clusters);
   cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = 2 * NP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -284,8 +315,9 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 }
 
 // bn in {128, 160, 192, 256}; weight-tile box = bn/2 rows
+// np = MMA pairs per cluster: 2 expects tmA encoded with 64-row boxes (linear layers only, BN 256).
 int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int np) {
   p.n_tiles = cdiv(p.N, bn);
   const int m_pairs = cdiv(m_tiles, 2);
   // output tensor map: [rows, out columns] (linear) or [B,H,W,out columns] (conv), 32-column boxes, 64B swizzle
@@ -312,6 +344,16 @@ int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap
   int epi = (p.bias ? EPI_BIAS : 0) | (p.rowvec ? EPI_ROWVEC : 0) | (p.residual ? EPI_RES : 0);
   if (p.act_gelu || !(epi == 0 || epi == EPI_BIAS || epi == (EPI_BIAS | EPI_ROWVEC) || epi == (EPI_BIAS | EPI_RES)))
     epi = EPI_RUNTIME;
+  if (np == 2) {
+    VTON_CHECK_ARG(!p.conv && bn == 256, "gemm2: the four-CTA cluster variant covers linear layers with BN 256 only");
+    if (geglu) return launch2<256, 5, true, 0, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
+    switch (epi) {
+      case 0: return launch2<256, 5, false, 0, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
+      case EPI_BIAS: return launch2<256, 5, false, EPI_BIAS, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
+      case EPI_BIAS | EPI_RES: return launch2<256, 5, false, EPI_BIAS | EPI_RES, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
+      default: return launch2<256, 5, false, EPI_RUNTIME, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
+    }
+  }
   if (geglu) {
     if (bn == 256) return launch2<256, 5, true, 0>(tmA, tmB, tmOut, p, m_pairs, stream);
     if (bn == 128) return launch2<128, 7, true, 0>(tmA, tmB, tmOut, p, m_pairs, stream);

@@ -8,6 +8,7 @@ both UNets, garment-feature attention, CFG and the DDPM update are libb200vton.s
 graph per step (denoise.TryOnDenoiser). Pre/post-processing (VAE, CLIP) is host-side PyTorch plumbing.
 """
 import inspect
+import os
 import types
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
@@ -50,6 +51,28 @@ def randn_tensor(shape, generator=None, device=None, dtype=None):
     if generator is not None and generator.device.type != device.type and generator.device.type == "cpu":
         rand_device = torch.device("cpu")
     return torch.randn(shape, generator=generator, device=rand_device, dtype=dtype).to(device)
+
+
+class _StageTrace:
+    """B200VTON_TRACE=1: device-time per pipeline stage (CUDA events), printed to stderr at the end of __call__."""
+
+    def __init__(self):
+        self.ev = [("start", self._rec())]
+
+    @staticmethod
+    def _rec():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def mark(self, name):
+        self.ev.append((name, self._rec()))
+
+    def report(self):
+        import sys
+        torch.cuda.synchronize()
+        parts = [f"{n}: {self.ev[i][1].elapsed_time(e):.1f} ms" for i, (n, e) in enumerate(self.ev[1:])]
+        print("[b200vton trace] " + " | ".join(parts), file=sys.stderr, flush=True)
 
 
 class StableDiffusionXLInpaintPipeline:
@@ -516,6 +539,7 @@ class StableDiffusionXLInpaintPipeline:
             batch_size = prompt_embeds.shape[0]
         device = self._execution_device
 
+        trace = _StageTrace() if os.environ.get("B200VTON_TRACE") else None
         # 3. prompt
         (prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds) = self.encode_prompt(
             prompt=prompt, prompt_2=prompt_2, device=device, num_images_per_prompt=num_images_per_prompt,
@@ -533,6 +557,8 @@ class StableDiffusionXLInpaintPipeline:
         latent_timestep = timesteps[:1].repeat(batch_size * num_images_per_prompt)
         is_strength_max = strength == 1.0
 
+        if trace:
+            trace.mark("prompt+timesteps")
         # 5. image / mask
         init_image = self.image_processor.preprocess(image, height=height, width=width).to(dtype=torch.float32)
         mask = self.mask_processor.preprocess(mask_image, height=height, width=width)
@@ -562,6 +588,8 @@ class StableDiffusionXLInpaintPipeline:
         pose_img = torch.cat([pose_img] * 2) if self.do_classifier_free_guidance else pose_img
         cloth = self._encode_vae_image(cloth.to(device=device, dtype=prompt_embeds.dtype), generator=generator)
 
+        if trace:
+            trace.mark("vae_encode(image, masked, pose, cloth)")
         # 9./10. added conditions
         height, width = latents.shape[-2:]
         height, width = height * self.vae_scale_factor, width * self.vae_scale_factor
@@ -591,6 +619,8 @@ class StableDiffusionXLInpaintPipeline:
         image_embeds = self.prepare_ip_adapter_image_embeds(ip_adapter_image, device, batch_size * num_images_per_prompt)
         image_embeds = self.unet.encoder_hid_proj(image_embeds).to(prompt_embeds.dtype)      # Resampler, once (:1726)
 
+        if trace:
+            trace.mark("clip_image_encoder+resampler")
         # 11. denoising loop on the B200 engine
         self._num_timesteps = len(timesteps)
         if self._denoiser is None:
@@ -600,6 +630,8 @@ class StableDiffusionXLInpaintPipeline:
                     image_embeds, text_embeds_cloth.to(device), guidance_scale=self.guidance_scale,
                     do_cfg=self.do_classifier_free_guidance)
         den.set_step_tables(self.scheduler, timesteps)
+        if trace:
+            trace.mark("denoiser.prepare (context K/V, garment passes)")
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(timesteps):
                 if self.interrupt:
@@ -618,6 +650,8 @@ class StableDiffusionXLInpaintPipeline:
                 if callback is not None and i % (callback_steps or 1) == 0:
                     callback(i, t, latents)
         latents = latents.clone()
+        if trace:
+            trace.mark("denoise loop")
 
         if not output_type == "latent":
             needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
@@ -626,6 +660,9 @@ class StableDiffusionXLInpaintPipeline:
         # NB (reference quirk, src/tryon_pipeline.py:1868-1885): with output_type == "latent", `image` is still the
         # caller's input image, and that is what gets returned.
         image = self.image_processor.postprocess(image, output_type=output_type)
+        if trace:
+            trace.mark("vae_decode+postprocess")
+            trace.report()
         self.maybe_free_model_hooks()
         self._last_latents = latents
         return (image,)
