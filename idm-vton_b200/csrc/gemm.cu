@@ -177,7 +177,8 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
-                   cudaStream_t stream, int np = 1);
+                   cudaStream_t stream, int np = 1, const CUtensorMap* tmS0 = nullptr, const CUtensorMap* tmS1 = nullptr,
+                   const CUtensorMap* tmBs = nullptr);
 
 // force_bn encoding: 0 = automatic kernel / tile choice; 64..256 = 1-CTA kernel (gemm.cu) with that tile width;
 // 1000 + {128,160,192,256} = 2-CTA persistent kernel (gemm2.cu) with that tile width.
@@ -201,12 +202,15 @@ static int pick_bn2(int N, bool geglu) {
 
 // Returns the 2-CTA tile width to use, or 0 for the 1-CTA kernel.
 static int choose_v2(int m_tiles, int N, bool geglu, bool has_shortcut, int force_bn) {
-  if (has_shortcut) return 0;   // the shortcut accumulator does not fit next to two accumulator stages
-  if (force_bn >= 1000) return force_bn - 1000;
-  if (force_bn != 0 || !g_auto_v2) return 0;
-  if (m_tiles < 4 || N < 128) return 0;
-  if (geglu && N % 128 != 0) return 0;
-  return pick_bn2(N, geglu);
+  int bn = 0;
+  if (force_bn >= 1000) {
+    bn = force_bn - 1000;
+  } else if (force_bn == 0 && g_auto_v2 && m_tiles >= 4 && N >= 128 && !(geglu && N % 128 != 0)) {
+    bn = pick_bn2(N, geglu);
+  }
+  // with a fused shortcut the tile carries two accumulators (one TMEM stage): widths whose pair fits 512 columns
+  if (has_shortcut && bn == 192) bn = (force_bn >= 1000) ? 0 : 160;
+  return bn;
 }
 
 static int pick_bn(int N, int force_bn) {
@@ -345,7 +349,7 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
     const int Csc = C0 + (sc1 ? C1 : 0);
     uint64_t dims[2] = {static_cast<uint64_t>(Csc), static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {static_cast<uint64_t>(Csc) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn2 ? bn / 2 : bn)};
     if (int e = encode_tmap_f16(&tmBs, w_sc, 2, dims, strides, box)) return e;
     p.slabs_sc = Csc / 64;
     p.sc_split = C0 / 64;
@@ -373,7 +377,7 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
   p.cin_slabs = Cin / 64;
   p.cout = Cout;
   const int m_tiles = p.tiles_x * p.tiles_y * cdiv(B, bb);
-  if (bn2) return gemm2_dispatch(bn, false, tmA, tmB, p, m_tiles, stream);
+  if (bn2) return gemm2_dispatch(bn, false, tmA, tmB, p, m_tiles, stream, 1, &tmS0, &tmS1, &tmBs);
   return dispatch(bn, false, tmA, tmB, tmS0, tmS1, tmBs, p, m_tiles, stream);
 }
 

@@ -34,10 +34,17 @@ struct Smem2 {
 // both pairs, so the L2 slices serve 24 KB instead of 32 KB per CTA and K slab — the chip-wide L2 output rate
 // (~6300 B/clk, 42 B/clk/SM) is what bounds these GEMMs at ~65% tensor-pipe utilisation, not the tensor cores.
 // A slot is recycled when BOTH pairs' MMAs have retired (empty barriers count NP multicast commits).
-template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1>
+// SC = the resnet's 1x1 shortcut conv rides along (conv mode only): after the 9*Cin/64 main slabs the producer streams
+// the Csc/64 slabs of the (two-source, never concatenated) block input and the MMAs accumulate them into a SECOND
+// accumulator at columns [BN, 2BN), so conv2 and conv_shortcut keep their separately rounded fp16 outputs. With two
+// accumulators per tile there is one TMEM stage instead of two; these tiles have >= 99 K slabs, so the exposed
+// epilogue is a few percent.
+template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1, bool SC = false>
 __global__ void __launch_bounds__(320, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmOut, const GemmParams p, int m_pairs) {
+             const __grid_constant__ CUtensorMap tmOut, const GemmParams p, int m_pairs,
+             const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
+             const __grid_constant__ CUtensorMap tmBs) {
   using L = Smem2<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -59,13 +66,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int n_clusters = gridDim.x / (2 * NP);
   const int n_super = (p.n_tiles + NP - 1) / NP;   // NP N-adjacent tiles per cluster step
   const int total_tiles = m_pairs * n_super;
-  const int slabs = p.slabs_main;
+  const int slabs = p.slabs_main + (SC ? p.slabs_sc : 0);
   constexpr uint32_t kTmemCols = 512;   // two accumulator stages of BN (<= 256) columns
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if (SC) {
+      tma_prefetch_desc(&tmS0);
+      tma_prefetch_desc(&tmS1);
+      tma_prefetch_desc(&tmBs);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), NP);   // one multicast commit per pair
@@ -105,7 +117,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t a_dst = smem_base + stage * L::STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);   // both CTAs' bytes
-          if (p.conv) {
+          if (SC && s >= p.slabs_main) {
+            const int ss = s - p.slabs_main;
+            if (ss < p.sc_split)
+              tma2_load_4d(a_dst, &tmS0, full_bar(stage), ss * BK, x0, y0, b0);
+            else
+              tma2_load_4d(a_dst, &tmS1, full_bar(stage), (ss - p.sc_split) * BK, x0, y0, b0);
+            tma2_load_2d(b_dst, &tmBs, full_bar(stage), ss * BK, n0);
+          } else if (p.conv) {
             const int tap = s / p.cin_slabs;
             const int c0 = (s - tap * p.cin_slabs) * BK;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -129,8 +148,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t it = 0;
       int tile_iter = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
-        const int acc = tile_iter & 1;
-        const uint32_t acc_phase = (tile_iter >> 1) & 1;
+        const int acc = SC ? 0 : (tile_iter & 1);
+        const uint32_t acc_phase = SC ? (tile_iter & 1) : ((tile_iter >> 1) & 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // both CTAs' epilogues drained this accumulator stage
         tc_fence_after();
         const uint32_t d = tmem_base + acc * BN;
@@ -142,10 +161,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t a_src = smem_base + stage * L::STAGE_BYTES;
           const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
+          const bool sc_slab = SC && s >= p.slabs_main;
+          const int s_local = sc_slab ? s - p.slabs_main : s;
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t a_desc = make_smem_desc_sw128(a_src + k * 32, 0, 1024);
             const uint64_t b_desc = make_smem_desc_sw128(b_src + k * 32, 0, 1024);
-            tc_mma_f16_2cta(d, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            tc_mma_f16_2cta(d + (sc_slab ? BN : 0), a_desc, b_desc, idesc, (s_local > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit_2cta(empty_bar(stage), NP == 2 ? 0xF : 0x3);   // this pair is done with the slot (all CTAs hear it)
         }
@@ -172,8 +193,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int qb = p.conv ? (quarter * 32) / (p.bw * p.bh) : 0;
     int tile_iter = 0;
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
-      const int acc = tile_iter & 1;
-      const uint32_t acc_phase = (tile_iter >> 1) & 1;
+      const int acc = SC ? 0 : (tile_iter & 1);
+      const uint32_t acc_phase = SC ? (tile_iter & 1) : ((tile_iter >> 1) & 1);
       const int n_tile = (t % n_super) * NP + static_cast<int>(pr);
       const int m_tile = 2 * (t / n_super) + static_cast<int>(rank);
       long long out_row;
@@ -221,7 +242,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t pk[16];
         if (PRE_RES) res_fetch(c + 2, rnxt);
         if (PRE_BIAS) bias_fetch(c + 2, bnxt);
-        epilogue_chunk<BN, GEGLU, EPI>(p, t_row, 0, n_tile, out_row, sample, c, pk, PRE_RES ? rcur : nullptr,
+        epilogue_chunk<BN, GEGLU, EPI>(p, t_row, SC ? BN : 0, n_tile, out_row, sample, c, pk, PRE_RES ? rcur : nullptr,
                                        PRE_BIAS ? bcur : nullptr);
         if (PRE_RES) {
 #pragma unroll
@@ -264,11 +285,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1>
+struct ScMaps {
+  const CUtensorMap* s0;
+  const CUtensorMap* s1;
+  const CUtensorMap* bs;
+};
+
+template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1, bool SC = false>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmParams& p,
-                   int m_pairs, cudaStream_t stream) {
+                   int m_pairs, cudaStream_t stream, ScMaps sc = ScMaps{nullptr, nullptr, nullptr}) {
   using L = Smem2<BN, STAGES>;
-  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI, NP>;
+  static_assert(!SC || 2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
+  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI, NP, SC>;
   static bool configured = false;
   static int max_clusters = kSMs / (2 * NP);
   if (!configured) {
@@ -309,7 +337,8 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  VTON_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p, m_pairs));
+  VTON_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p, m_pairs, sc.s0 ? *sc.s0 : tmA, sc.s1 ? *sc.s1 : tmA,
+                               sc.bs ? *sc.bs : tmB));
   count_launch();
   return kOk;
 }
@@ -317,7 +346,8 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 // bn in {128, 160, 192, 256}; weight-tile box = bn/2 rows
 // np = MMA pairs per cluster: 2 expects tmA encoded with 64-row boxes (linear layers only, BN 256).
 int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
-                   cudaStream_t stream, int np) {
+                   cudaStream_t stream, int np, const CUtensorMap* tmS0, const CUtensorMap* tmS1,
+                   const CUtensorMap* tmBs) {
   p.n_tiles = cdiv(p.N, bn);
   const int m_pairs = cdiv(m_tiles, 2);
   // output tensor map: [rows, out columns] (linear) or [B,H,W,out columns] (conv), 32-column boxes, 64B swizzle
@@ -344,6 +374,17 @@ int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap
   int epi = (p.bias ? EPI_BIAS : 0) | (p.rowvec ? EPI_ROWVEC : 0) | (p.residual ? EPI_RES : 0);
   if (p.act_gelu || !(epi == 0 || epi == EPI_BIAS || epi == (EPI_BIAS | EPI_ROWVEC) || epi == (EPI_BIAS | EPI_RES)))
     epi = EPI_RUNTIME;
+  if (p.slabs_sc) {   // conv + fused 1x1 shortcut: runtime epilogue, one TMEM stage, weight-tile box of tmBs = bn/2 rows
+    VTON_CHECK_ARG(p.conv && !geglu && np == 1 && tmS0 && tmS1 && tmBs, "gemm2: shortcut slabs need conv mode and their maps");
+    const ScMaps sc{tmS0, tmS1, tmBs};
+    switch (bn) {
+      case 128: return launch2<128, 7, false, EPI_RUNTIME, 1, true>(tmA, tmB, tmOut, p, m_pairs, stream, sc);
+      case 160: return launch2<160, 6, false, EPI_RUNTIME, 1, true>(tmA, tmB, tmOut, p, m_pairs, stream, sc);
+      case 256: return launch2<256, 5, false, EPI_RUNTIME, 1, true>(tmA, tmB, tmOut, p, m_pairs, stream, sc);
+    }
+    set_last_error("gemm2: shortcut variant supports BN 128/160/256 (got %d)", bn);
+    return kErrUnsupported;
+  }
   if (np == 2) {
     VTON_CHECK_ARG(!p.conv && bn == 256, "gemm2: the four-CTA cluster variant covers linear layers with BN 256 only");
     if (geglu) return launch2<256, 5, true, 0, 2>(tmA, tmB, tmOut, p, m_pairs, stream);

@@ -514,3 +514,41 @@ def test_cross_attention_ip_scale_and_peaky(lib):
     out = lib.cross_attention(q, kt, vt, ki, vi, heads=H, ip_scale=0.5)
     ref = r16(r16(_attn_ref(q, kt, vt, H, 0.125)) + r16(0.5 * r16(_attn_ref(q, ki, vi, H, 0.125))))
     close(out, ref, tol=3e-3)
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,force_bn", [(2, 32, 24, 640, 320, 640, 1160), (2, 32, 24, 640, 320, 640, 1128),
+                                                      (4, 32, 24, 1280, 1280, 1280, 1256), (1, 32, 24, 320, 0, 640, 0),
+                                                      (3, 16, 24, 1280, 640, 1280, 0), (2, 64, 48, 640, 320, 320, 0)])
+def test_conv3x3_shortcut_2cta_variants(lib, B, H, W, C0, C1, Cout, force_bn):
+    """Resnet conv2 with the fused 1x1 shortcut on the 2-CTA kernel (second TMEM accumulator, one accumulator stage):
+    against the fp32 reference with the reference's rounding (both conv outputs rounded to fp16, then added) and
+    against the 1-CTA kernel."""
+    from idm_vton_b200.engine import pack_conv3x3
+    h = rnd(B, H, W, Cout, seed=1)
+    s0 = rnd(B, H, W, C0, seed=2)
+    s1 = rnd(B, H, W, C1, seed=3) if C1 else None
+    w = rnd(Cout, Cout, 3, 3, scale=(9 * Cout) ** -0.5, seed=4)
+    wsc = rnd(Cout, C0 + C1, scale=(C0 + C1) ** -0.5, seed=5)
+    b2, bsc = rnd(Cout, seed=6), rnd(Cout, seed=7)
+    wp = pack_conv3x3(w)
+    out = lib.conv3x3(h, wp, bias=b2, sc0=s0, sc1=s1, w_sc=wsc, bias_sc=bsc, force_bn=force_bn)
+    cat = (torch.cat([s0, s1], -1) if C1 else s0).float()
+    ref = r16(r16(cat @ wsc.float().t() + bsc.float()) + r16(_conv_ref(h, w, b2)))
+    close(out, ref)
+    v1 = lib.conv3x3(h, wp, bias=b2, sc0=s0, sc1=s1, w_sc=wsc, bias_sc=bsc, force_bn=128)
+    close(out, v1, tol=1e-3)
+
+
+def test_gemm_four_cta_cluster_variant(lib):
+    """force_bn = 2256: the 2-CTA kernel in four-CTA clusters with multicast A slabs (off by default: measured slower).
+    Must be bit-identical to the two-CTA-cluster launch, including odd N-tile counts and ragged M."""
+    from idm_vton_b200.engine import pack_geglu
+    for (M, N, K) in [(1024, 1280, 256), (3000, 768, 192), (2048, 512, 1280)]:
+        a, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
+        o4 = lib.gemm(a, w, bias=b, residual=r, force_bn=2256)
+        o2 = lib.gemm(a, w, bias=b, residual=r, force_bn=1256)
+        assert torch.equal(o4, o2)
+        close(o4, r16(r16(a.float() @ w.float().t() + b.float()) + r.float()))
+    a, w, b = rnd(1024, 640, seed=5), rnd(5120, 640, scale=640 ** -0.5, seed=6), rnd(5120, seed=7)
+    wp, bp = pack_geglu(w, b, 256)
+    assert torch.equal(lib.gemm(a, wp, bias=bp, geglu=True, force_bn=2256), lib.gemm(a, wp, bias=bp, geglu=True, force_bn=1256))
