@@ -296,7 +296,13 @@ int attn5_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensor
 static int g_attn_v2 = 1;   // 1: use the ping-pong kernels for Nq >= 256
 int attn6_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                  const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, int q_tiles, cudaStream_t stream);
+                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, int q_tiles, int poly,
+                 cudaStream_t stream);
+// attn6: exponentials (of every 4) evaluated by the FMA-pipe polynomial instead of the SFU. Measured on B200
+// (profiles/r1_attention_poly_exp.jsonl): 0 -> 695, 1 -> 683, 2 -> 573 TFLOP/s at the 3072-token level: the extra FMA-pipe
+// issue slots cost more than the SFU slots they free, so the default is 0.
+static int g_attn_poly = 0;
+void set_attn_poly(int n) { g_attn_poly = n; }
 static int g_attn_qtiles = 0;  // attn6: query tiles per CTA (0 = by K/V length, 1, 2)
 void set_attn_qtiles(int n) { g_attn_qtiles = n; }
 static int g_attn_ptmem = 2;  // 2: decoupled P-in-TMEM kernel (attn6.cu); 1: attn5.cu (P aliased onto S); 0: P through smem
@@ -339,7 +345,7 @@ int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long
       return attn6_launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
                           has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,
                           has1 ? static_cast<const int*>(kv1_base) : nullptr, scale * 1.4426950408889634f, accumulate,
-                          g_attn_qtiles, stream);
+                          g_attn_qtiles, g_attn_poly, stream);
     auto launch = g_attn_h2 ? (g_attn_ptmem ? attn5_launch : (g_attn_w16 ? attn4_launch : attn3_launch)) : attn2_launch;
     return launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
                         has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,

@@ -57,6 +57,20 @@ __device__ __forceinline__ float ex2k_(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (no SFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, an order below the fp16 rounding of P that follows), n added into the exponent field.
+// POLY of every 4 exponentials can be evaluated here instead of the SFU (the trade FlashAttention-4 describes); on B200
+// at d = 64 it measured slower (695 / 683 / 573 TFLOP/s for POLY = 0 / 1 / 2), so POLY = 0 is the default.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float xr = x + 12582912.f;   // 1.5 * 2^23: the integer nearest to x now sits in the low mantissa bits
+  const float n = xr - 12582912.f;
+  const float f = x - n;
+  float p = fmaf(f, 0.05517132f, 0.24261054f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992812f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate) {
@@ -67,7 +81,7 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-template <int G>
+template <int G, int POLY>
 __global__ void __launch_bounds__(A6Cfg<G>::THREADS, (G == 1) ? 2 : 1)
 attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
              const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -279,8 +293,10 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         for (int i = 0; i < 16; i += 2) {
           const float e0 = ex2k_(__uint_as_float(s[c][2 * i]) * sl2 - msc);
           const float e1 = ex2k_(__uint_as_float(s[c][2 * i + 1]) * sl2 - msc);
-          const float e2 = ex2k_(__uint_as_float(s[c][2 * i + 2]) * sl2 - msc);
-          const float e3 = ex2k_(__uint_as_float(s[c][2 * i + 3]) * sl2 - msc);
+          const float x2 = __uint_as_float(s[c][2 * i + 2]) * sl2 - msc;
+          const float x3 = __uint_as_float(s[c][2 * i + 3]) * sl2 - msc;
+          const float e2 = POLY >= 1 ? ex2_poly(x2) : ex2k_(x2);
+          const float e3 = POLY >= 2 ? ex2_poly(x3) : ex2k_(x3);
           l0 += e0;
           l1 += e1;
           l2 += e2;
@@ -375,7 +391,8 @@ attn6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
 int attn6_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                  const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, int q_tiles, cudaStream_t stream) {
+                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, int q_tiles, int poly,
+                 cudaStream_t stream) {
   Attn6Params p{};
   p.out = out;
   p.ld_out = ld_out;
@@ -389,25 +406,35 @@ int attn6_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensor
   p.kv1_base = kv1_base;
   p.scale_log2 = scale_log2;
   p.accumulate = accumulate;
+  if (q_tiles == 0) q_tiles = 1;
+  if (poly < 0 || poly > 2) poly = 0;
   static bool configured = false;
   if (!configured) {
-    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<1>::SMEM_TOTAL));
-    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<2>::SMEM_TOTAL));
+    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<1>::SMEM_TOTAL));
+    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<1>::SMEM_TOTAL));
+    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<1>::SMEM_TOTAL));
+    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<2>::SMEM_TOTAL));
+    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<2>::SMEM_TOTAL));
+    VTON_CUDA(cudaFuncSetAttribute(attn6_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A6Cfg<2>::SMEM_TOTAL));
     configured = true;
   }
+  auto go = [&](auto kern, auto cfg_tag) -> int {
+    using Cfg = decltype(cfg_tag);
+    constexpr int rows = (Cfg::THREADS - 64);   // 128 query rows per softmax group
+    dim3 grid((Nq + rows - 1) / rows, H, B);
+    VTON_CUDA(launch_kernel(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM_TOTAL, stream, tmQ, tmK0, tmV0, tmK1, tmV1, p));
+    return kOk;
+  };
   // Two query tiles per CTA share every K/V tile (half the L2 -> smem traffic), but two independent one-tile CTAs per
   // SM hide each other's prologue, epilogue and softmax bubbles: measured faster at every config-2 shape (L1
   // self+garment 644 vs 632 TFLOP/s, L2 422 vs 368, garment batch-16 728 vs 644 / 513 vs 412), so it is the default.
-  if (q_tiles == 0) q_tiles = 1;
+  int rc;
   if (q_tiles == 1) {
-    dim3 grid((Nq + 127) / 128, H, B);
-    VTON_CUDA(launch_kernel(attn6_kernel<1>, grid, dim3(A6Cfg<1>::THREADS), A6Cfg<1>::SMEM_TOTAL, stream, tmQ, tmK0, tmV0,
-                            tmK1, tmV1, p));
+    rc = poly == 0 ? go(attn6_kernel<1, 0>, A6Cfg<1>{}) : poly == 1 ? go(attn6_kernel<1, 1>, A6Cfg<1>{}) : go(attn6_kernel<1, 2>, A6Cfg<1>{});
   } else {
-    dim3 grid((Nq + 255) / 256, H, B);
-    VTON_CUDA(launch_kernel(attn6_kernel<2>, grid, dim3(A6Cfg<2>::THREADS), A6Cfg<2>::SMEM_TOTAL, stream, tmQ, tmK0, tmV0,
-                            tmK1, tmV1, p));
+    rc = poly == 0 ? go(attn6_kernel<2, 0>, A6Cfg<2>{}) : poly == 1 ? go(attn6_kernel<2, 1>, A6Cfg<2>{}) : go(attn6_kernel<2, 2>, A6Cfg<2>{});
   }
+  if (rc) return rc;
   count_launch();
   VTON_CUDA(cudaGetLastError());
   return kOk;

@@ -37,6 +37,7 @@ void set_attn_h2(int on);
 void set_attn_w16(int on);
 void set_attn_ptmem(int on);
 void set_attn_qtiles(int n);
+void set_attn_poly(int n);
 int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const void* latents, const void* noise,
                   const void* coef, int do_cfg, void* out, cudaStream_t stream);
 }  // namespace vton
@@ -59,6 +60,10 @@ int b200vton_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "programmatic_launch") == 0) {
     vton::set_pdl(value);
+    return 0;
+  }
+  if (name && strcmp(name, "attention_poly_exp") == 0) {
+    vton::set_attn_poly(value);
     return 0;
   }
   if (name && strcmp(name, "attention_q_tiles") == 0) {

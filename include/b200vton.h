@@ -33,7 +33,8 @@ long long b200vton_launch_count(void);
  * "attention_fp16_exp" = 1 (default) selects the ping-pong variant whose softmax evaluates exp2 two elements per SFU
  * op on fp16 arguments and lets the tensor core accumulate the row sums; 0 selects the fp32-softmax variant.
  * "attention_p_in_tmem" = 2 (default) selects the decoupled P-in-TMEM kernel (fp32 softmax, S issued one tile ahead);
- * ("attention_q_tiles" = 1 | 2 pins its query tiles per CTA, 0 = chosen from the K/V length);
+ * ("attention_q_tiles" = 1 | 2 pins its query tiles per CTA, 0 = chosen from the K/V length; "attention_poly_exp" =
+ * 0 | 1 | 2 of every 4 exponentials evaluated by an FMA-pipe polynomial instead of the SFU, default 0: measured slower);
  * 1 the packed-half kernel with P aliased onto its S columns; with 0,
  * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one.
  * "gemm_cluster4" = 1 runs large linear layers with 256-wide tiles in four-CTA clusters whose CTA pairs multicast the

@@ -552,3 +552,24 @@ def test_gemm_four_cta_cluster_variant(lib):
     a, w, b = rnd(1024, 640, seed=5), rnd(5120, 640, scale=640 ** -0.5, seed=6), rnd(5120, seed=7)
     wp, bp = pack_geglu(w, b, 256)
     assert torch.equal(lib.gemm(a, wp, bias=bp, geglu=True, force_bn=2256), lib.gemm(a, wp, bias=bp, geglu=True, force_bn=1256))
+
+
+def test_attention_polynomial_exp_fraction(lib):
+    """attn6.cu evaluates 0, 1 or 2 of every 4 exponentials with the FMA-pipe polynomial (default 0): all three against
+    the fp32 reference on a diffuse and on a peaky distribution with a ragged two-segment K/V stream."""
+    Bp, H, N, Ng = 1, 3, 520, 700
+    C = H * 64
+    for qscale in (1.0, 5.0):
+        q, k, v = rnd(2 * Bp, N, C, scale=qscale, seed=41), rnd(2 * Bp, N, C, seed=42), rnd(2 * Bp, N, C, seed=43)
+        gk, gv = rnd(Bp, Ng, C, seed=44), rnd(Bp, Ng, C, seed=45)
+        ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gk], 1), torch.cat([v[Bp:], gv], 1), H, 0.125)
+        ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
+        errs = []
+        try:
+            for n in (0, 1, 2):
+                lib.set_option("attention_poly_exp", n)
+                o = lib.attention(q, k, v, gk, gv, kv1_off=Bp, heads=H)
+                errs.append((close(o[Bp:], ref_c, tol=3e-3), close(o[:Bp], ref_u, tol=3e-3)))
+        finally:
+            lib.set_option("attention_poly_exp", 0)
+        print(f"qscale {qscale}: errors (cond, uncond) for poly 0/1/2: {errs}")
