@@ -11,6 +11,8 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
                  const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
                  cudaStream_t stream);
+int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
+                     cudaStream_t stream);
 int cross_attn_impl(const void* q, long long ldq, const void* kt, const void* vt, long long ldkv_t, int Nt,
                     const void* ki, const void* vi, long long ldkv_i, int Ni, void* out, long long ldo, int B, int H,
                     int Nq, float scale, float ip_scale, cudaStream_t stream);
@@ -118,6 +120,11 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
                              int H, int Nq, float scale, float ip_scale, void* stream) {
   return vton::cross_attn_impl(q, ldq, kt, vt, ldkv_t, Nt, ki, vi, ldkv_i, Ni, out, ldo, B, H, Nq, scale, ip_scale,
                                S(stream));
+}
+
+int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                               void* out, void* stream) {
+  return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, out, S(stream));
 }
 
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,

@@ -42,8 +42,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
+static int encode_tmap_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                           int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -69,7 +70,7 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
       }
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, gbox, gel, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -79,6 +80,17 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
     return kErrCuda;
   }
   return kOk;
+}
+
+int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
+  return encode_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box, elem_strides,
+                         swizzle_bytes);
+}
+
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  return encode_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, nullptr, 128);
 }
 
 }  // namespace vton

@@ -38,6 +38,10 @@ const char* get_last_error();
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, const uint32_t* elem_strides = nullptr, int swizzle_bytes = 128);
 
+// fp32 elements, SWIZZLE_128B (inner box = 32 floats = 128 B): the TF32 convolution of the VAE.
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // Programmatic dependent launch (option "programmatic_launch", default on): the hot kernels are launched with

@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i,
                            _vp],
     "b200vton_cross_attention": [_vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _f, _vp],
+    "b200vton_conv3x3_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
     "b200vton_nchw_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -179,6 +180,31 @@ def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=No
                                 out.stride(1), B, H, Nq, N0, n1, B1, kv1_off, kv1_mod, _p(kv1_base), float(scale),
                                 int(accumulate), _stream())
     _check(rc, "b200vton_attention")
+    return out
+
+
+def conv3x3_f32_supported(x, cin, cout):
+    """Shapes the TF32 convolution kernel covers (everything else stays on the caller's fallback)."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and cin % 32 == 0 and cout % 32 == 0 and cout >= 64
+            and x.shape[3] % 8 == 0)
+
+
+def pack_conv3x3_f32(weight):
+    """[Cout,Cin,3,3] fp32 -> [9,Cout,Cin] (tap-major rows for the kernel's weight map)."""
+    return weight.detach().permute(2, 3, 0, 1).reshape(9, weight.shape[0], weight.shape[1]).contiguous()
+
+
+def conv3x3_f32(x, w_packed, bias=None):
+    """x: logical [B,Cin,H,W] fp32 (any strides; converted to channels_last = NHWC memory); returns a channels_last
+    [B,Cout,H,W] fp32 tensor."""
+    lib = load()
+    B, Cin, H, W = x.shape
+    Cout = w_packed.shape[1]
+    assert w_packed.dtype == torch.float32 and w_packed.is_contiguous() and w_packed.shape == (9, Cout, Cin)
+    x = x.contiguous(memory_format=torch.channels_last)
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    rc = lib.b200vton_conv3x3_nhwc_f32(_p(x), B, H, W, Cin, _p(w_packed), Cout, _p(bias), _p(out), _stream())
+    _check(rc, "b200vton_conv3x3_nhwc_f32")
     return out
 
 

@@ -4,15 +4,44 @@ The reference pipeline receives a diffusers `AutoencoderKL` as a component (src/
 `vae.encode(x).latent_dist.sample(generator)`, `vae.decode(z, return_dict=False)[0]`, `vae.config.{scaling_factor,
 force_upcast,latent_channels,block_out_channels}` (:911-932,1646,1868-1880). diffusers is not installable in this image, so
 this module supplies an architecture-compatible VAE (same parameter names as diffusers 0.25.0's AutoencoderKL, restated
-from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): it is
-executed by PyTorch/cuDNN here and will move onto the engine's conv / GroupNorm kernels after the denoise loop.
+from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): its 3x3
+convolutions have an engine kernel (`_conv` -> `b200vton_conv3x3_nhwc_f32`, TF32 tensor cores, opt-in: see the note at
+`_ENGINE_CONV`); norms, the mid-block attention, resampling and the tiny-channel convolutions are PyTorch.
 """
+import os
 import types
 
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+# Measured on B200 (profiles/r1_vae_tf32_conv.jsonl): the kernel beats cuDNN on every VAE convolution shape (478-809 vs
+# 349-643 TFLOP/s), but the VAE as a whole got SLOWER (encode 78 vs 63 ms, decode 138 vs 107 ms per 2 images): the
+# convolutions are only ~15% of its time, the rest is fp32 GroupNorm / SiLU / resampling / attention passes over up to
+# 805 MB tensors, and feeding an NHWC kernel from torch's NCHW GroupNorm adds two layout copies per convolution. The
+# switch therefore stays off until those passes have NHWC kernels of their own (B200VTON_VAE_TF32_CONV=1 to enable).
+_ENGINE_CONV = os.environ.get("B200VTON_VAE_TF32_CONV", "0") == "1"
+
+
+def _conv(conv, x):
+    """3x3 / stride 1 / pad 1 fp32 convolutions with 32-aligned channel counts run on the engine's TF32 tensor-core
+    kernel on CUDA (`b200vton_conv3x3_nhwc_f32`: TF32 products, fp32 accumulation — the arithmetic class cuDNN uses for
+    fp32 convolutions under torch's default `allow_tf32`); every other case (CPU, fp16, conv_in / conv_out with 3-8
+    channels, stride-2 downsamplers, 1x1 shortcuts, TF32 disabled by the caller) stays on `nn.Conv2d`."""
+    if (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+            and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            and torch.backends.cudnn.allow_tf32 and _ENGINE_CONV):
+        from . import lib as L
+        if L.conv3x3_f32_supported(x, conv.in_channels, conv.out_channels):
+            key = (conv.weight.data_ptr(), conv.weight._version)
+            cache = getattr(conv, "_b200_packed", None)
+            if cache is None or cache[0] != key:
+                cache = (key, L.pack_conv3x3_f32(conv.weight))
+                conv._b200_packed = cache
+            return L.conv3x3_f32(x, cache[1], conv.bias)
+    return conv(x)
 
 
 class _Resnet(nn.Module):
@@ -25,8 +54,8 @@ class _Resnet(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = _conv(self.conv1, F.silu(self.norm1(x)))
+        h = _conv(self.conv2, F.silu(self.norm2(h)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -92,7 +121,7 @@ class _Up(nn.Module):
         for r in self.resnets:
             x = r(x)
         if self.upsamplers is not None:
-            x = self.upsamplers[0].conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+            x = _conv(self.upsamplers[0].conv, F.interpolate(x, scale_factor=2.0, mode="nearest"))
         return x
 
 

@@ -94,6 +94,14 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
                              const void* ki, const void* vi, int64_t ldkv_i, int Ni, void* out, int64_t ldo, int B,
                              int H, int Nq, float scale, float ip_scale, void* stream);
 
+/* fp32 3x3 convolution, stride 1, zero padding 1, on the TF32 tensor cores (TF32 products, fp32 accumulate, fp32 bias,
+ * fp32 out — the arithmetic class PyTorch uses for fp32 cuDNN convolutions by default): the VAE's convolutions
+ * (diffusers AutoencoderKL ResnetBlock2D.conv1/conv2, Upsample2D.conv; the reference runs the SDXL VAE in fp32,
+ * src/tryon_pipeline.py:913-915,1076-1093). x: [B,H,W,Cin] dense NHWC (= channels_last memory), w: [9][Cout][Cin]
+ * (tap-major), bias: [Cout] or NULL, out: [B,H,W,Cout]. Cin, Cout multiples of 32, Cout >= 64, W divisible by 8. */
+int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                               void* out, void* stream);
+
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
  * fp32 statistics (deterministic two-stage reduction, no atomics), optional SiLU, fp16 out [B*HW, C0+C1].
  * stats_ws: max(B,296)*64 doubles of scratch.

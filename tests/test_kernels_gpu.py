@@ -573,3 +573,24 @@ def test_attention_polynomial_exp_fraction(lib):
         finally:
             lib.set_option("attention_poly_exp", 0)
         print(f"qscale {qscale}: errors (cond, uncond) for poly 0/1/2: {errs}")
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(1, 128, 128, 128, 96), (2, 256, 128, 64, 48), (1, 512, 512, 32, 24),
+                                            (2, 512, 256, 37, 24), (1, 128, 256, 50, 40), (3, 64, 64, 16, 8)])
+def test_conv3x3_fp32_tf32(lib, B, Cin, Cout, H, W):
+    """b200vton_conv3x3_nhwc_f32 (the VAE's convolutions): against cuDNN's full-fp32 convolution (TF32 off) as the
+    exact result, with cuDNN's own TF32 path beside it — same arithmetic class, so both must sit within TF32 rounding.
+    Ragged H, several pixel-box shapes, both tile widths."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (9 * Cin) ** -0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    assert lib.conv3x3_f32_supported(x, Cin, Cout)
+    out = lib.conv3x3_f32(x, lib.pack_conv3x3_f32(w), b)
+    assert out.shape == (B, Cout, H, W) and out.is_contiguous(memory_format=torch.channels_last)
+    with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+        ref = torch.nn.functional.conv2d(x, w, b, padding=1)
+    e_ours = close(out, ref, tol=2e-3)
+    with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=True):
+        e_cudnn = close(torch.nn.functional.conv2d(x, w, b, padding=1), ref, tol=2e-3)
+    print(f"tf32 conv err vs fp32: ours {e_ours:.2e}, cuDNN-TF32 {e_cudnn:.2e}")
