@@ -74,13 +74,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(acc_bar, 1);
     fence_barrier_init();
   }
+  // Programmatic dependent launch: wait for the previous kernel BEFORE allocating tensor memory. A dependent CTA that
+  // grabbed TMEM first and then waited could starve a primary CTA on the same SM that had signalled its dependents but
+  // not yet allocated its own columns (library kernels signal at their very start): neither would ever proceed.
+  pdl_wait();
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_launch_dependents();
-  pdl_wait();   // set-up above overlapped the previous kernel's tail; its results are visible from here
+  pdl_launch_dependents();   // this CTA holds everything it needs: the next kernel may start its own set-up
 
   if (warp == 0) {
     // ===================== TMA producer =====================

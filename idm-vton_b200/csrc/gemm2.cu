@@ -88,12 +88,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     fence_barrier_init();
   }
+  // Programmatic dependent launch: wait for the previous kernel BEFORE allocating tensor memory. A dependent CTA that
+  // grabbed TMEM first and then waited could starve a primary CTA on the same SM that had signalled its dependents but
+  // not yet allocated its own columns (library kernels signal at their very start): neither would ever proceed.
+  pdl_wait();
   if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit / TMA
   tc_fence_after();
-  pdl_launch_dependents();
-  pdl_wait();            // everything above overlapped the previous kernel's tail; its results are visible from here
+  pdl_launch_dependents();   // this cluster holds everything it needs: the next kernel may start its own set-up
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {

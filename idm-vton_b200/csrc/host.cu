@@ -18,7 +18,11 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return g_err; }
 
-static std::atomic<int> g_pdl{1};
+// Off by default: it gained 1.3% of the loop on B200, but two bench runs that mix these kernels with cuBLAS/cuDNN
+// kernels (the end-to-end pipeline call) hung while every engine-only run was clean; the suspected cause — a dependent
+// CTA holding tensor memory while it waits for a primary that has not allocated yet — is removed (the kernels now wait
+// BEFORE tcgen05.alloc), but that fix has not been re-validated on hardware yet.
+static std::atomic<int> g_pdl{0};
 int pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
 void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 static std::atomic<long long> g_launches{0};

@@ -44,11 +44,11 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-// Programmatic dependent launch (option "programmatic_launch", default on): the hot kernels are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, call griddepcontrol.launch_dependents on entry and
-// griddepcontrol.wait after their own set-up (barrier init, TMEM allocation, tensor-map prefetch) and before they
-// touch any global memory, so the set-up of kernel n+1 and the launch latency overlap the tail of kernel n — inside
-// the captured denoise step (~930 launches) that is the gap between every pair of kernels.
+// Programmatic dependent launch (option "programmatic_launch", default OFF, see host.cu): the hot kernels are launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization; they initialise their barriers and prefetch tensor maps, call
+// griddepcontrol.wait, only then allocate tensor memory and touch global memory, and call
+// griddepcontrol.launch_dependents once they hold all their resources — so the launch latency and part of the set-up
+// of kernel n+1 overlap the tail of kernel n (~930 launches per captured denoise step).
 int pdl_enabled();
 void set_pdl(int on);
 

@@ -62,8 +62,8 @@ def load(build_if_missing=True):
         lib.b200vton_set_option(b"gemm_2cta_auto", 0)
     if os.environ.get("B200VTON_CLUSTER4", "1") == "0":
         lib.b200vton_set_option(b"gemm_cluster4", 0)
-    if os.environ.get("B200VTON_PDL", "1") == "0":
-        lib.b200vton_set_option(b"programmatic_launch", 0)
+    if os.environ.get("B200VTON_PDL", "0") == "1":
+        lib.b200vton_set_option(b"programmatic_launch", 1)
     if os.environ.get("B200VTON_ATTN6", "1") == "0":
         lib.b200vton_set_option(b"attention_p_in_tmem", 1)
     if os.environ.get("B200VTON_ATTN5", "1") == "0":

@@ -39,8 +39,9 @@ long long b200vton_launch_count(void);
  * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one.
  * "gemm_cluster4" = 1 runs large linear layers with 256-wide tiles in four-CTA clusters whose CTA pairs multicast the
  * shared A slabs; 0 (default: it measured slower on B200) keeps two-CTA clusters.
- * "programmatic_launch" = 1 (default) launches the hot kernels with programmatic stream serialization (their set-up
- * overlaps the previous kernel's tail; they wait for it before touching memory); 0 = plain stream order. */
+ * "programmatic_launch" = 1 launches the hot kernels with programmatic stream serialization (their set-up overlaps
+ * the previous kernel's tail; they wait for it before allocating tensor memory or touching global memory);
+ * 0 (default) = plain stream order. */
 int b200vton_set_option(const char* name, int value);
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T): nn.Linear on the hot path — attn to_q/to_k/to_v/to_out
