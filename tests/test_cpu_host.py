@@ -306,3 +306,45 @@ def test_vae_and_image_processor_plumbing():
     assert set(m.unique().tolist()) <= {0.0, 1.0}
     pil = ip.postprocess(torch.zeros(1, 3, 8, 8), output_type="pil")
     assert pil[0].size == (8, 8)
+
+
+def test_library_options_and_argument_checks_without_gpu():
+    """Every option name the header documents is accepted, unknown names are rejected with a message, and the new entry
+    points validate their arguments before any CUDA work (error code 1 + message, no crash, no GPU needed)."""
+    from idm_vton_b200 import lib
+    l = lib.load()
+    header = open(os.path.join(ROOT, "include", "b200vton.h")).read()
+    block = header[header.index("/* library options:"):header.index("int b200vton_set_option")]
+    names = sorted(set(re.findall(r'"([a-z0-9_]+)"', block)))
+    assert {"gemm_2cta_auto", "gemm_cluster4", "programmatic_launch", "attention_p_in_tmem", "attention_q_tiles",
+            "attention_poly_exp"} <= set(names)
+    defaults = {"gemm_2cta_auto": 1, "gemm_cluster4": 0, "programmatic_launch": 0, "attention_pingpong": 1,
+                "attention_fp16_exp": 1, "attention_p_in_tmem": 2, "attention_q_tiles": 0, "attention_poly_exp": 0,
+                "attention_16_warps": 1}
+    for n in names:
+        assert n in defaults, f"option {n} documented in the header but not covered here"
+        assert l.b200vton_set_option(n.encode(), defaults[n]) == 0
+    assert l.b200vton_set_option(b"no_such_option", 1) != 0 and b"unknown option" in l.b200vton_last_error()
+    # fused cross-attention: context sizes beyond one score tile are refused (the engine then uses the 2-launch path)
+    rc = l.b200vton_cross_attention(None, 64, None, None, 64, 81, None, None, 0, 0, None, 64, 1, 1, 128, 0.125, 1.0, None)
+    assert rc == 1 and b"Nt <= 80" in l.b200vton_last_error()
+    rc = l.b200vton_cross_attention(None, 64, None, None, 64, 77, None, None, 64, 17, None, 64, 1, 1, 128, 0.125, 1.0, None)
+    assert rc == 1
+    # fp32/TF32 convolution: channel alignment
+    rc = l.b200vton_conv3x3_nhwc_f32(None, 1, 16, 16, 48, None, 64, None, None, None)
+    assert rc == 1 and b"multiples of 32" in l.b200vton_last_error()
+
+
+def test_vae_conv_dispatch_and_weight_packing_on_cpu():
+    """The VAE's engine-convolution switch never engages on CPU tensors (plain nn.Conv2d result), and the fp32 weight
+    packing is the tap-major [9, Cout, Cin] layout the kernel's weight map expects."""
+    import idm_vton_b200.vae as V
+    from idm_vton_b200 import lib
+    conv = torch.nn.Conv2d(32, 64, 3, padding=1)
+    x = torch.randn(1, 32, 8, 8)
+    assert torch.equal(V._conv(conv, x), conv(x))
+    assert not lib.conv3x3_f32_supported(x, 32, 64)                       # CPU tensor
+    wp = lib.pack_conv3x3_f32(conv.weight)
+    assert wp.shape == (9, 64, 32) and wp.is_contiguous()
+    for tap in (0, 4, 8):
+        assert torch.equal(wp[tap], conv.weight[:, :, tap // 3, tap % 3])
