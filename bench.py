@@ -497,7 +497,7 @@ def run_b200(args, rank, world, local):
             emit({"value": None, "unit": "images/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                   "unavailable": f"e2e section did not finish within {e2e_limit:.0f} s"})
         sys.stdout.flush()
-        os._exit(0 if rank == 0 else 1)
+        os._exit(0)     # a degraded but valid result: the line above carries everything except e2e
 
     guard_timer = threading.Timer(e2e_limit + (0 if rank == 0 else 20), _give_up)
     guard_timer.daemon = True
