@@ -13,6 +13,8 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
                  cudaStream_t stream);
 int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
                      cudaStream_t stream);
+int groupnorm_f32_impl(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps, int silu,
+                       void* stats_ws, long long stats_ws_doubles, void* out, cudaStream_t stream);
 int cross_attn_impl(const void* q, long long ldq, const void* kt, const void* vt, long long ldkv_t, int Nt,
                     const void* ki, const void* vi, long long ldkv_i, int Ni, void* out, long long ldo, int B, int H,
                     int Nq, float scale, float ip_scale, cudaStream_t stream);
@@ -125,6 +127,11 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
 int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                                void* out, void* stream) {
   return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, out, S(stream));
+}
+
+int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps,
+                                 int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, void* stream) {
+  return vton::groupnorm_f32_impl(x, B, HW, C, gamma, beta, eps, silu, stats_ws, stats_ws_doubles, out, S(stream));
 }
 
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,

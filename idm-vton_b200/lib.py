@@ -23,6 +23,7 @@ SIGNATURES = {
                            _vp],
     "b200vton_cross_attention": [_vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _f, _vp],
     "b200vton_conv3x3_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
+    "b200vton_groupnorm_nhwc_f32": [_vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i64, _vp, _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
     "b200vton_nchw_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -205,6 +206,27 @@ def conv3x3_f32(x, w_packed, bias=None):
     out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
     rc = lib.b200vton_conv3x3_nhwc_f32(_p(x), B, H, W, Cin, _p(w_packed), Cout, _p(bias), _p(out), _stream())
     _check(rc, "b200vton_conv3x3_nhwc_f32")
+    return out
+
+
+_gn32_ws = {}
+
+
+def groupnorm_f32_nhwc(x, gamma, beta, eps, silu):
+    """x: logical [B,C,H,W] fp32 in channels_last memory (= dense NHWC); returns the same layout. EXPERIMENTAL."""
+    lib = load()
+    B, C, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn32_ws.get(key)
+    need = 64 * max(B, 1184)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float64, device=x.device)
+        _gn32_ws[key] = ws
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    rc = lib.b200vton_groupnorm_nhwc_f32(_p(x), B, H * W, C, _p(gamma), _p(beta), float(eps), int(silu), _p(ws),
+                                         ws.numel(), _p(out), _stream())
+    _check(rc, "b200vton_groupnorm_nhwc_f32")
     return out
 
 

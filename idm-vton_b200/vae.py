@@ -23,6 +23,27 @@ import torch.nn.functional as F
 # 805 MB tensors, and feeding an NHWC kernel from torch's NCHW GroupNorm adds two layout copies per convolution. The
 # switch therefore stays off until those passes have NHWC kernels of their own (B200VTON_VAE_TF32_CONV=1 to enable).
 _ENGINE_CONV = os.environ.get("B200VTON_VAE_TF32_CONV", "0") == "1"
+# EXPERIMENTAL (written at the end of round 1, not yet run on hardware): keep the whole VAE in NHWC (channels_last) so
+# that the engine convolution needs no layout copies, with GroupNorm(+SiLU) on `b200vton_groupnorm_nhwc_f32`.
+_ENGINE_NHWC = os.environ.get("B200VTON_VAE_NHWC", "0") == "1"
+
+
+def _use_nhwc(x):
+    return _ENGINE_NHWC and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+
+
+def _gn(norm, x, silu):
+    """GroupNorm (+ SiLU). NHWC mode: fp32 channels_last tensors go to the engine's fp32 GroupNorm kernel."""
+    if _use_nhwc(x) and norm.num_groups == 32 and x.shape[1] % 32 == 0 and x.shape[1] <= 2048:
+        from . import lib as L
+        x = x.contiguous(memory_format=torch.channels_last)
+        return L.groupnorm_f32_nhwc(x, norm.weight, norm.bias, norm.eps, silu)
+    y = norm(x)
+    return F.silu(y) if silu else y
+
+
+def _conv_device_ok(x):
+    return x.is_cuda
 
 
 def _conv(conv, x):
@@ -30,9 +51,9 @@ def _conv(conv, x):
     kernel on CUDA (`b200vton_conv3x3_nhwc_f32`: TF32 products, fp32 accumulation — the arithmetic class cuDNN uses for
     fp32 convolutions under torch's default `allow_tf32`); every other case (CPU, fp16, conv_in / conv_out with 3-8
     channels, stride-2 downsamplers, 1x1 shortcuts, TF32 disabled by the caller) stays on `nn.Conv2d`."""
-    if (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+    if (_conv_device_ok(x) and x.dtype == torch.float32 and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
             and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
-            and torch.backends.cudnn.allow_tf32 and _ENGINE_CONV):
+            and torch.backends.cudnn.allow_tf32 and (_ENGINE_CONV or _ENGINE_NHWC)):
         from . import lib as L
         if L.conv3x3_f32_supported(x, conv.in_channels, conv.out_channels):
             key = (conv.weight.data_ptr(), conv.weight._version)
@@ -54,8 +75,8 @@ class _Resnet(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = _conv(self.conv1, F.silu(self.norm1(x)))
-        h = _conv(self.conv2, F.silu(self.norm2(h)))
+        h = _conv(self.conv1, _gn(self.norm1, x, True))
+        h = _conv(self.conv2, _gn(self.norm2, h, True))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -72,10 +93,15 @@ class _Attn(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
-        t = self.group_norm(x).view(b, c, h * w).transpose(1, 2)
+        if _use_nhwc(x):                                   # tokens are a free view of the NHWC tensor
+            t = _gn(self.group_norm, x, False).permute(0, 2, 3, 1).reshape(b, h * w, c)
+        else:
+            t = self.group_norm(x).view(b, c, h * w).transpose(1, 2)
         q, k, v = self.to_q(t), self.to_k(t), self.to_v(t)
         o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
         o = self.to_out[0](o)
+        if _use_nhwc(x):
+            return x + o.reshape(b, h, w, c).permute(0, 3, 1, 2)
         return x + o.transpose(1, 2).reshape(b, c, h, w)
 
 
@@ -140,7 +166,7 @@ class _Encoder(nn.Module):
         for d in self.down_blocks:
             x = d(x)
         x = self.mid_block(x)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
+        return self.conv_out(_gn(self.conv_norm_out, x, True))
 
 
 class _Decoder(nn.Module):
@@ -158,7 +184,7 @@ class _Decoder(nn.Module):
         x = self.mid_block(self.conv_in(z))
         for u in self.up_blocks:
             x = u(x)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
+        return self.conv_out(_gn(self.conv_norm_out, x, True))
 
 
 class DiagonalGaussianDistribution:
@@ -199,13 +225,20 @@ class AutoencoderKL(nn.Module):
         return next(self.parameters()).device
 
     def encode(self, x, return_dict=True):
+        if _use_nhwc(x):
+            x = x.contiguous(memory_format=torch.channels_last)
+            dist = DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)).contiguous())
+            return types.SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
         dist = DiagonalGaussianDistribution(self.quant_conv(self.encoder(x)))
         return types.SimpleNamespace(latent_dist=dist) if return_dict else (dist,)
 
     def decode(self, z, return_dict=True, generator=None):
         # (cuDNN's channels_last kernels and its autotuner were both measured on B200 for these fp32 convolutions:
         # channels_last is slower — encode 221 vs 173 ms, decode 150 vs 113 ms per call — and autotuning changes nothing)
-        img = self.decoder(self.post_quant_conv(z))
+        if _use_nhwc(z):
+            img = self.decoder(self.post_quant_conv(z.contiguous(memory_format=torch.channels_last))).contiguous()
+        else:
+            img = self.decoder(self.post_quant_conv(z))
         return types.SimpleNamespace(sample=img) if return_dict else (img,)
 
     def enable_slicing(self):

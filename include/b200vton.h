@@ -103,6 +103,13 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
 int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                                void* out, void* stream);
 
+/* fp32 GroupNorm(32 groups)(+SiLU) over dense NHWC [B,HW,C] fp32 — the VAE's norms (diffusers AutoencoderKL
+ * ResnetBlock2D.norm1/norm2 + SiLU, Attention.group_norm, conv_norm_out), deterministic two-stage statistics.
+ * gamma/beta: [C] fp32 or NULL. stats_ws: scratch of stats_ws_doubles doubles, at least 64 * max(B, 1184) is always
+ * enough. EXPERIMENTAL in round 1 (not yet run on hardware; nothing calls it unless B200VTON_VAE_NHWC=1). */
+int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps,
+                                 int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, void* stream);
+
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
  * fp32 statistics (deterministic two-stage reduction, no atomics), optional SiLU, fp16 out [B*HW, C0+C1].
  * stats_ws: max(B,296)*64 doubles of scratch.

@@ -348,3 +348,51 @@ def test_vae_conv_dispatch_and_weight_packing_on_cpu():
     assert wp.shape == (9, 64, 32) and wp.is_contiguous()
     for tap in (0, 4, 8):
         assert torch.equal(wp[tap], conv.weight[:, :, tap // 3, tap % 3])
+
+
+def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
+    """The experimental NHWC route through the VAE (engine GroupNorm + TF32 convolution kernels, B200VTON_VAE_NHWC=1)
+    with the two kernels replaced by PyTorch stand-ins that honour the same layout contract (channels_last in and
+    out, packed [9,Cout,Cin] weights): layout handling, the token view of the mid-block attention and the residual
+    adds must reproduce the default path."""
+    import idm_vton_b200.vae as V
+    from idm_vton_b200 import lib
+
+    def fake_gn(x, gamma, beta, eps, silu):
+        assert x.is_contiguous(memory_format=torch.channels_last)
+        y = torch.nn.functional.group_norm(x, 32, gamma, beta, eps)
+        y = torch.nn.functional.silu(y) if silu else y
+        return y.contiguous(memory_format=torch.channels_last)
+
+    def fake_conv(x, w_packed, bias=None):
+        cout, cin = w_packed.shape[1], w_packed.shape[2]
+        w = w_packed.reshape(3, 3, cout, cin).permute(2, 3, 0, 1)
+        return torch.nn.functional.conv2d(x, w, bias, padding=1).contiguous(memory_format=torch.channels_last)
+
+    torch.manual_seed(0)
+    vae = V.AutoencoderKL(block_out_channels=(32, 64), layers_per_block=1).eval()
+    x = torch.rand(2, 3, 32, 24) * 2 - 1
+    with torch.no_grad():
+        ref_mean = vae.encode(x).latent_dist.mean
+        z = torch.randn(2, 4, 16, 12)
+        ref_img = vae.decode(z).sample
+        monkeypatch.setattr(V, "_use_nhwc", lambda t: t.dim() == 4 and t.dtype == torch.float32)
+        monkeypatch.setattr(V, "_ENGINE_NHWC", True)
+        monkeypatch.setattr(lib, "groupnorm_f32_nhwc", fake_gn)
+        monkeypatch.setattr(lib, "conv3x3_f32", fake_conv)
+        monkeypatch.setattr(lib, "conv3x3_f32_supported", lambda t, cin, cout: cin % 32 == 0 and cout % 32 == 0 and cout >= 64)
+        monkeypatch.setattr(V, "_conv_device_ok", lambda t: True)
+        calls = {"conv": 0}
+        real_fake = fake_conv
+
+        def counting_conv(x, w_packed, bias=None):
+            calls["conv"] += 1
+            return real_fake(x, w_packed, bias)
+
+        monkeypatch.setattr(lib, "conv3x3_f32", counting_conv)
+        got_mean = vae.encode(x).latent_dist.mean
+        got_img = vae.decode(z).sample
+    assert calls["conv"] > 0, "the engine-convolution route was not taken"
+    assert got_mean.shape == ref_mean.shape and got_img.shape == ref_img.shape and got_img.is_contiguous()
+    assert (got_mean - ref_mean).abs().max() < 1e-4
+    assert (got_img - ref_img).abs().max() < 1e-4
