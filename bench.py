@@ -391,6 +391,7 @@ def run_b200(args, rank, world, local):
     n0 = L.launch_count()
     den.capture()
     launches_per_denoise_step = (L.launch_count() - n0) // 2     # capture() = one eager warm-up + one recorded pass
+    log(f"denoise step captured ({launches_per_denoise_step} launches per step)")
     if args.profile_one_step:
         # for `ncu --profile-from-start off`: exactly one denoise step (graph replay) inside the profiler range
         den.step(0, torch.zeros_like(den.latents), use_graph=True)
@@ -405,6 +406,7 @@ def run_b200(args, rank, world, local):
         out = run_loop()
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all(), "non-finite latents"
+    log(f"{args.warmup} warm-up loops done")
 
     def barrier():
         if world > 1:
@@ -432,6 +434,7 @@ def run_b200(args, rank, world, local):
         total_ms = tt.item()
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms / 1e3)
+    log(f"timed region done: {ms_per_step:.1f} ms per loop, {value:.3f} images/s")
 
     # ---- rank 0: roofline inputs and the CPU baseline (before the e2e section, so that a line can be printed even if
     # the e2e section does not come back)
@@ -448,6 +451,7 @@ def run_b200(args, rank, world, local):
             except Exception as ex:  # pragma: no cover
                 cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
     clocks_summary = clocks.summary()
+    log("dominant-kernel timing / cpu baseline done; entering the e2e section" if not args.no_e2e else "no e2e section")
 
     def emit(e2e):
         line = {
@@ -537,6 +541,7 @@ def run_b200(args, rank, world, local):
             return images.cpu()                      # D2H read of the result
 
         imgs = call()                                 # warm-up (cuDNN autotune, graph re-capture for this request)
+        log("e2e warm-up call done")
         d2h = imgs.numel() * imgs.element_size()
         barrier()
         t1 = time.time()
