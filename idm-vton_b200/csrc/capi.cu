@@ -36,6 +36,7 @@ int skinny_linear_impl(const void* x, int ldx, int M, int K, const void* W, long
                        cudaStream_t stream);
 void set_auto_v2(int on);
 void set_cluster4(int on);
+void set_gemm_deep(int on);
 void set_attn_v2(int on);
 void set_attn_h2(int on);
 void set_attn_w16(int on);
@@ -56,6 +57,10 @@ long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_2cta_auto") == 0) {
     vton::set_auto_v2(value);
+    return 0;
+  }
+  if (name && strcmp(name, "gemm_deep_pipeline") == 0) {
+    vton::set_gemm_deep(value);
     return 0;
   }
   if (name && strcmp(name, "gemm_cluster4") == 0) {

@@ -39,6 +39,8 @@ long long b200vton_launch_count(void);
  * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one.
  * "gemm_cluster4" = 1 runs large linear layers with 256-wide tiles in four-CTA clusters whose CTA pairs multicast the
  * shared A slabs; 0 (default: it measured slower on B200) keeps two-CTA clusters.
+ * "gemm_deep_pipeline" = 1 (EXPERIMENTAL, default 0, not yet run on hardware) gives the 256-wide 2-CTA tiles a sixth
+ * operand stage in exchange for a one-slot epilogue staging ring.
  * "programmatic_launch" = 1 launches the hot kernels with programmatic stream serialization (their set-up overlaps
  * the previous kernel's tail; they wait for it before allocating tensor memory or touching global memory);
  * 0 (default) = plain stream order. */
