@@ -277,23 +277,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
-int attn2_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
-                 const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream);
-
-int attn3_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
-                 const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream);
-
-int attn4_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
-                 const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream);
-
-int attn5_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
-                 const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
-                 int kv1_count, const int* kv1_base, float scale_log2, int accumulate, cudaStream_t stream);
-
-static int g_attn_v2 = 1;   // 1: use the ping-pong kernels for Nq >= 256
+static int g_attn_v2 = 1;   // 1: attn6.cu (pipelined, P in tensor memory) for Nq >= 256; 0: this one-tile kernel always
 int attn6_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                  const CUtensorMap& tmV1, __half* out, int ld_out, int B, int H, int Nq, int N0, int N1, int kv1_off,
                  int kv1_count, const int* kv1_base, float scale_log2, int accumulate, int q_tiles, int poly,
@@ -305,13 +289,7 @@ static int g_attn_poly = 0;
 void set_attn_poly(int n) { g_attn_poly = n; }
 static int g_attn_qtiles = 0;  // attn6: query tiles per CTA (0 = by K/V length, 1, 2)
 void set_attn_qtiles(int n) { g_attn_qtiles = n; }
-static int g_attn_ptmem = 2;  // 2: decoupled P-in-TMEM kernel (attn6.cu); 1: attn5.cu (P aliased onto S); 0: P through smem
-void set_attn_ptmem(int on) { g_attn_ptmem = on; }
-static int g_attn_w16 = 1;  // 1: 16-softmax-warp variant (attn4.cu) of the packed-half kernel
-void set_attn_w16(int on) { g_attn_w16 = on; }
-static int g_attn_h2 = 1;   // 1: packed-half softmax variant (attn3.cu), 0: fp32 softmax variant (attn2.cu)
 void set_attn_v2(int on) { g_attn_v2 = on; }
-void set_attn_h2(int on) { g_attn_h2 = on; }
 
 static int encode_tokens(CUtensorMap* tm, const void* base, long long ld, int cols, int n, int batch) {
   uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(n), static_cast<uint64_t>(batch)};
@@ -341,15 +319,10 @@ int attn_impl(const void* q, long long ldq, const void* k0, const void* v0, long
     if (int e = encode_tokens(&tmV1, v1, ldkv1, H * 64, N1, B1)) return e;
   }
   if (g_attn_v2 && Nq >= 256) {
-    if (g_attn_ptmem == 2)
-      return attn6_launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
+    return attn6_launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
                           has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,
                           has1 ? static_cast<const int*>(kv1_base) : nullptr, scale * 1.4426950408889634f, accumulate,
                           g_attn_qtiles, g_attn_poly, stream);
-    auto launch = g_attn_h2 ? (g_attn_ptmem ? attn5_launch : (g_attn_w16 ? attn4_launch : attn3_launch)) : attn2_launch;
-    return launch(tmQ, tmK0, tmV0, tmK1, tmV1, static_cast<__half*>(out), static_cast<int>(ldo), B, H, Nq, N0, N1,
-                        has1 ? kv1_off : (N1 > 0 ? B : 0), has1 ? (kv1_mod > 0 ? kv1_mod : B1) : 1,
-                        has1 ? static_cast<const int*>(kv1_base) : nullptr, scale * 1.4426950408889634f, accumulate, stream);
   }
   AttnParams p{};
   p.out = static_cast<__half*>(out);

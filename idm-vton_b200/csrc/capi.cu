@@ -38,9 +38,6 @@ void set_auto_v2(int on);
 void set_cluster4(int on);
 void set_gemm_deep(int on);
 void set_attn_v2(int on);
-void set_attn_h2(int on);
-void set_attn_w16(int on);
-void set_attn_ptmem(int on);
 void set_attn_qtiles(int n);
 void set_attn_poly(int n);
 int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const void* latents, const void* noise,
@@ -51,7 +48,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
 
 extern "C" {
 
-int b200vton_version(void) { return 100; }
+int b200vton_version(void) { return 101; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
@@ -77,18 +74,6 @@ int b200vton_set_option(const char* name, int value) {
   }
   if (name && strcmp(name, "attention_q_tiles") == 0) {
     vton::set_attn_qtiles(value);
-    return 0;
-  }
-  if (name && strcmp(name, "attention_p_in_tmem") == 0) {
-    vton::set_attn_ptmem(value);
-    return 0;
-  }
-  if (name && strcmp(name, "attention_16_warps") == 0) {
-    vton::set_attn_w16(value);
-    return 0;
-  }
-  if (name && strcmp(name, "attention_fp16_exp") == 0) {
-    vton::set_attn_h2(value);
     return 0;
   }
   if (name && strcmp(name, "attention_pingpong") == 0) {

@@ -12,6 +12,41 @@ import torch
 from .engine import CIN_PAD, UNetEngine
 
 
+def ddpm_step_coefficients(scheduler, t):
+    """(sqrt(1-abar_t), 1/sqrt(abar_t), x0 coeff, x_t coeff, sigma_t) of DDPMScheduler.step at timestep t, computed in
+    fp32 torch like diffusers does, from the GENERIC scheduler interface only — `alphas_cumprod`,
+    `config.num_train_timesteps`, `num_inference_steps` (and `previous_timestep` when the object has it) — so the
+    caller's own `diffusers.DDPMScheduler` works (inference.py passes `DDPMScheduler.from_pretrained(...)`). The fused
+    kernel implements epsilon prediction with fixed_small variance and no clipping / thresholding: anything else raises."""
+    cfg = getattr(scheduler, "config", None)
+    get = (lambda k, d=None: cfg.get(k, d)) if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+    if get("prediction_type", "epsilon") != "epsilon" or get("variance_type", "fixed_small") != "fixed_small" \
+            or get("clip_sample", False) or get("thresholding", False):
+        raise NotImplementedError("the fused CFG+DDPM step covers epsilon prediction, fixed_small variance, no "
+                                  "clip_sample / thresholding (the IDM-VTON scheduler config)")
+    if not hasattr(scheduler, "alphas_cumprod"):
+        raise TypeError(f"{type(scheduler).__name__} has no alphas_cumprod: the engine needs a DDPM-family scheduler")
+    t = int(t)
+    n_train = int(get("num_train_timesteps", len(scheduler.alphas_cumprod)))
+    if hasattr(scheduler, "previous_timestep"):
+        prev_t = int(scheduler.previous_timestep(t))
+    else:
+        steps = getattr(scheduler, "num_inference_steps", None) or n_train
+        prev_t = t - n_train // steps
+    ac = scheduler.alphas_cumprod.to(device="cpu", dtype=torch.float32)
+    a_t = ac[t]
+    a_prev = ac[prev_t] if prev_t >= 0 else torch.tensor(1.0)
+    b_t, b_prev = 1 - a_t, 1 - a_prev
+    cur_a = a_t / a_prev
+    cur_b = 1 - cur_a
+    c0 = (a_prev ** 0.5 * cur_b) / b_t
+    c1 = cur_a ** 0.5 * b_prev / b_t
+    var = torch.clamp((1 - a_prev) / (1 - a_t) * cur_b, min=1e-20)
+    sigma = var ** 0.5 if t > 0 else torch.tensor(0.0)
+    inv_sa = torch.tensor(1.0, dtype=torch.float32) / (a_t ** 0.5)
+    return float(b_t ** 0.5), float(inv_sa), float(c0), float(c1), float(sigma)
+
+
 class TryOnDenoiser:
     def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=8):
         """hoist_garment: the garment UNet depends on the timestep but not on the latents, so all
@@ -76,7 +111,7 @@ class TryOnDenoiser:
         """Uploads the per-step scalars: t and {gs, sqrt(1-abar), 1/sqrt(abar), c0, c1, sigma}."""
         rows = []
         for t in timesteps:
-            rows.append([self.guidance_scale, *scheduler.step_coefficients(int(t))])
+            rows.append([self.guidance_scale, *ddpm_step_coefficients(scheduler, int(t))])
         self.coef_table = torch.tensor(rows, dtype=torch.float32, device=self.device)
         self.t_table = torch.tensor([float(int(t)) for t in timesteps], dtype=torch.float32, device=self.device)
         self.base_table = torch.arange(len(rows), dtype=torch.int32, device=self.device) * self.Bg

@@ -74,7 +74,7 @@ class _Resnet:
 
 class _Block:
     __slots__ = ("ln1w", "ln1b", "wqkv", "wo1", "bo1", "ln2w", "ln2b", "wq2", "wkv_txt", "wkv_ip", "wo2", "bo2", "ln3w",
-                 "ln3b", "wff1", "bff1", "wff2", "bff2", "c", "heads", "ff_bn")
+                 "ln3b", "wff1", "bff1", "wff2", "bff2", "c", "heads", "ff_bn", "ip_scale")
 
 
 class _T2D:
@@ -92,7 +92,9 @@ class UNetEngine:
 
     GEGLU_BN = 256
 
-    def __init__(self, cfg, state_dict, kind, device="cuda"):
+    def __init__(self, cfg, state_dict, kind, device="cuda", ip_scales=None):
+        """ip_scales: optional {"<transformer block path>": scale} of the installed IPAttnProcessor2_0 instances
+        (ip_adapter/attention_processor.py:1995 `hidden + self.scale * ip_hidden`; default 1.0)."""
         from . import lib
         lib.load()
         self.L = lib
@@ -103,6 +105,7 @@ class UNetEngine:
         self.temb_dim = self.ch[0] * 4
         self.cross = cfg["cross_attention_dim"]
         self.ip_tokens = cfg["ip_tokens"] if kind == "tryon" else 0
+        self.ip_scales = dict(ip_scales or {})
         self._pack(state_dict)
 
     # -------------------------------------------------------------------------------------------
@@ -147,6 +150,7 @@ class UNetEngine:
             blk.wkv_txt = torch.cat([self._w(sd, f"{b}.attn2.to_k.weight"), self._w(sd, f"{b}.attn2.to_v.weight")],
                                     0).contiguous()
             blk.wkv_ip = None
+            blk.ip_scale = float(self.ip_scales.get(b, 1.0))
             if self.ip_tokens:
                 blk.wkv_ip = torch.cat([self._w(sd, f"{b}.attn2.processor.to_k_ip.weight"),
                                         self._w(sd, f"{b}.attn2.processor.to_v_ip.weight")], 0).contiguous()
@@ -250,8 +254,13 @@ class UNetEngine:
         dim = self.cfg["addition_time_embed_dim"]
         te = L.timestep_embedding(time_ids.flatten().to(torch.float32).contiguous(), dim).view(b, -1)
         add = torch.cat([text_embeds.to(torch.float16), te], dim=-1).contiguous()
-        h = L.skinny_linear(add, self.ae[0], self.ae[1], out_silu=True)
-        return L.skinny_linear(h, self.ae[2], self.ae[3], out=out)
+        if out is None:
+            out = torch.empty((b, self.ae[2].shape[0]), dtype=torch.float16, device=self.device)
+        for r0 in range(0, b, 16):                          # the skinny-linear kernel takes <= 16 rows per launch
+            r1 = min(b, r0 + 16)
+            h = L.skinny_linear(add[r0:r1], self.ae[0], self.ae[1], out_silu=True)
+            L.skinny_linear(h, self.ae[2], self.ae[3], out=out[r0:r1])
+        return out
 
     # -------------------------------------------------------------------------------------------
     # per-step pieces
@@ -322,10 +331,11 @@ class UNetEngine:
         if kv_t.shape[1] <= 80 and (kv_i is None or kv_i.shape[1] <= 16):
             # text + image-token cross-attention fused in one launch (both key sets fit one score tile)
             a2 = L.cross_attention(q2, kv_t[..., :C], kv_t[..., C:], None if kv_i is None else kv_i[..., :C],
-                                   None if kv_i is None else kv_i[..., C:], heads=H)
+                                   None if kv_i is None else kv_i[..., C:], heads=H, ip_scale=blk.ip_scale)
         else:
             a2 = L.attention(q2, kv_t[..., :C], kv_t[..., C:], heads=H)
             if kv_i is not None:
+                assert blk.ip_scale == 1.0, "ip scale != 1 needs the fused cross-attention kernel"
                 L.attention(q2, kv_i[..., :C], kv_i[..., C:], heads=H, accumulate=True, out=a2)
         h = L.gemm(a2.view(B * N, C), blk.wo2, bias=blk.bo2, residual=h)
         n3 = L.layernorm(h, blk.ln3w, blk.ln3b)

@@ -36,25 +36,36 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 101      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
 
 
 def load(build_if_missing=True):
-    """Load (building first if needed) libb200vton.so and declare every exported symbol."""
+    """Load (building first if needed) libb200vton.so and declare every exported symbol. The build runs under an
+    exclusive file lock (several ranks may import at once); a library whose sources changed and that cannot be rebuilt,
+    or whose ABI version differs from this binding, raises instead of being called with a stale argument layout."""
     global _lib
     if _lib is not None:
         return _lib
     if build_if_missing:
         from . import build as _build
-        try:
-            _build.build()
-        except Exception:
-            if not os.path.exists(LIB_PATH):
-                raise
+        if _build.needs_build():
+            import fcntl
+            os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
+            with open(os.path.join(_HERE, "build", ".lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    _build.build()          # re-checks the source hash under the lock
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: the CUDA extension must be built (python idm-vton_b200/build.py); "
                            "there is no CPU fallback")
     lib = ctypes.CDLL(LIB_PATH)
     lib.b200vton_version.restype = _i
+    got = lib.b200vton_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} reports ABI version {got}, this binding expects {ABI_VERSION}: rebuild it "
+                           "(python idm-vton_b200/build.py --force)")
     lib.b200vton_last_error.restype = _c.c_char_p
     lib.b200vton_launch_count.restype = _c.c_longlong
     lib.b200vton_set_option.argtypes = [_c.c_char_p, _i]
@@ -67,14 +78,6 @@ def load(build_if_missing=True):
         lib.b200vton_set_option(b"gemm_deep_pipeline", 1)
     if os.environ.get("B200VTON_PDL", "0") == "1":
         lib.b200vton_set_option(b"programmatic_launch", 1)
-    if os.environ.get("B200VTON_ATTN6", "1") == "0":
-        lib.b200vton_set_option(b"attention_p_in_tmem", 1)
-    if os.environ.get("B200VTON_ATTN5", "1") == "0":
-        lib.b200vton_set_option(b"attention_p_in_tmem", 0)
-    if os.environ.get("B200VTON_ATTN4", "1") == "0":
-        lib.b200vton_set_option(b"attention_16_warps", 0)
-    if os.environ.get("B200VTON_ATTN3", "1") == "0":
-        lib.b200vton_set_option(b"attention_fp16_exp", 0)
     if os.environ.get("B200VTON_ATTN2", "1") == "0":
         lib.b200vton_set_option(b"attention_pingpong", 0)
     for name, args in SIGNATURES.items():

@@ -53,6 +53,12 @@ def randn_tensor(shape, generator=None, device=None, dtype=None):
     return torch.randn(shape, generator=generator, device=rand_device, dtype=dtype).to(device)
 
 
+def _weights_version(module):
+    """Changes whenever a parameter of `module` is replaced or written in place (load_state_dict, .to(), optimizer
+    steps): keys the caches derived from its weights (fp32 VAE twin, unconditional CLIP tokens)."""
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
 class _StageTrace:
     """B200VTON_TRACE=1: device-time per pipeline stage (CUDA events), printed to stderr at the end of __call__."""
 
@@ -217,7 +223,7 @@ class StableDiffusionXLInpaintPipeline:
             hs = hs.repeat_interleave(num_images_per_prompt, dim=0)
             # the unconditional branch encodes an all-zero image: the same tensor for every call with this encoder,
             # so it is computed once per (shape, dtype, device) and reused
-            key = (tuple(image.shape), image.dtype, str(image.device))
+            key = (tuple(image.shape), image.dtype, str(image.device), id(self.image_encoder), _weights_version(self.image_encoder))
             if getattr(self, "_uncond_clip_key", None) != key:
                 self._uncond_clip = self.image_encoder(torch.zeros_like(image), output_hidden_states=True).hidden_states[-2]
                 self._uncond_clip_key = key
@@ -354,9 +360,10 @@ class StableDiffusionXLInpaintPipeline:
         if self.vae.dtype == torch.float32:
             return self.vae
         twin = getattr(self, "_vae_fp32", None)
-        if twin is None or twin[0] is not self.vae or twin[1].device != self.vae.device:
+        ver = _weights_version(self.vae)
+        if twin is None or twin[0] is not self.vae or twin[1].device != self.vae.device or twin[2] != ver:
             import copy
-            twin = (self.vae, copy.deepcopy(self.vae).to(dtype=torch.float32))
+            twin = (self.vae, copy.deepcopy(self.vae).to(dtype=torch.float32), ver)
             self._vae_fp32 = twin
         return twin[1]
 
@@ -623,8 +630,11 @@ class StableDiffusionXLInpaintPipeline:
             trace.mark("clip_image_encoder+resampler")
         # 11. denoising loop on the B200 engine
         self._num_timesteps = len(timesteps)
-        if self._denoiser is None:
-            self._denoiser = TryOnDenoiser(self.unet.engine(), self.unet_encoder.engine())
+        # unet.engine() re-packs after load_state_dict() / .to() on the module; a denoiser built on older engines (and its
+        # captured graph) would silently run stale weights
+        eng_t, eng_g = self.unet.engine(), self.unet_encoder.engine()
+        if self._denoiser is None or self._denoiser.tryon is not eng_t or self._denoiser.garment is not eng_g:
+            self._denoiser = TryOnDenoiser(eng_t, eng_g)
         den = self._denoiser
         den.prepare(latents, mask, masked_image_latents, pose_img, cloth, prompt_embeds, add_text_embeds, add_time_ids,
                     image_embeds, text_embeds_cloth.to(device), guidance_scale=self.guidance_scale,

@@ -73,6 +73,32 @@ class DDPMScheduler:
         steps = self.num_inference_steps if self.num_inference_steps else self.config.num_train_timesteps
         return t - self.config.num_train_timesteps // steps
 
+    def step(self, model_output, timestep, sample, generator=None, return_dict=True):
+        """diffusers DDPMScheduler.step (epsilon prediction, fixed_small variance) on the host in plain torch — the
+        arithmetic the reference loop runs at src/tryon_pipeline.py:1823. The engine does NOT call this (its per-step
+        update is the fused `b200vton_cfg_ddpm_step` kernel fed by `step_coefficients`); it exists so this object is a
+        complete scheduler for callers that step it themselves (e.g. the reference pipeline in oracle/make_golden_pipeline.py)."""
+        t = int(timestep)
+        prev_t = self.previous_timestep(t)
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        cur_a = a_t / a_prev
+        cur_b = 1 - cur_a
+        pred_original_sample = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+        pred_prev_sample = (a_prev ** 0.5 * cur_b) / b_t * pred_original_sample + cur_a ** 0.5 * b_prev / b_t * sample
+        self._last_noise = None
+        if t > 0:
+            dev = model_output.device
+            rand_dev = "cpu" if (generator is not None and generator.device.type == "cpu" and dev.type != "cpu") else dev
+            noise = torch.randn(model_output.shape, generator=generator, device=rand_dev, dtype=model_output.dtype).to(dev)
+            var = torch.clamp((1 - a_prev) / (1 - a_t) * cur_b, min=1e-20)
+            pred_prev_sample = pred_prev_sample + (var ** 0.5) * noise
+            self._last_noise = noise
+        if not return_dict:
+            return (pred_prev_sample,)
+        return type("DDPMSchedulerOutput", (), dict(prev_sample=pred_prev_sample, pred_original_sample=pred_original_sample))()
+
     def step_coefficients(self, t):
         """(sqrt(1-abar_t), 1/sqrt(abar_t), x0 coeff, x_t coeff, sigma_t) as python floats, computed in fp32 torch
         exactly like DDPMScheduler.step / _get_variance."""

@@ -15,6 +15,7 @@ import types
 import torch
 import torch.nn as nn
 
+from .attention_processor import Attention, AttnProcessor2_0, IPAttnProcessor2_0
 from .engine import CIN_PAD, SDXL_GARMENT, SDXL_TRYON, UNetEngine
 
 
@@ -210,13 +211,35 @@ class _Node(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover
         raise RuntimeError("container module")
 
+    def __getitem__(self, i):          # `attn.to_out[0]` (a ModuleList in the reference)
+        return self._modules[str(i)]
 
-def _register(root, key, tensor):
+
+def _heads_of(cfg, key):
+    """Attention heads of the block a parameter name belongs to (attention_head_dim per level, App. A)."""
+    nh = tuple(cfg["num_heads"])
+    if key.startswith("mid_block"):
+        return nh[-1]
+    if key.startswith("up_blocks."):
+        return nh[::-1][int(key.split(".")[1])]
+    return nh[int(key.split(".")[1])]
+
+
+def _register(root, key, tensor, cfg=None):
+    """Registers `tensor` under the reference's dotted parameter name. Path components `attn1` / `attn2` become
+    `Attention` containers (seam B3) and `attn2.processor` an `IPAttnProcessor2_0` owning `to_k_ip` / `to_v_ip`."""
     parts = key.split(".")
     m = root
-    for name in parts[:-1]:
+    for d, name in enumerate(parts[:-1]):
         if name not in m._modules:
-            m.add_module(name, _Node())
+            if name in ("attn1", "attn2") and cfg is not None and "transformer_blocks" in parts:
+                child = Attention(heads=_heads_of(cfg, key), _empty=True)
+            elif name == "processor" and isinstance(m, Attention):
+                child = IPAttnProcessor2_0(hidden_size=tensor.shape[0], cross_attention_dim=tensor.shape[1], scale=1.0,
+                                           num_tokens=cfg["ip_tokens"], device="meta")
+            else:
+                child = _Node()
+            m.add_module(name, child)
         m = m._modules[name]
     m.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
 
@@ -250,7 +273,10 @@ class _UNetBase(nn.Module):
                 shp, device=device, dtype=dtype)
             if tuple(t.shape) != tuple(shp):
                 raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(t.shape)}")
-            _register(self, k, t)
+            _register(self, k, t, self._cfg)
+        for m in self.modules():
+            if isinstance(m, Attention) and "processor" not in m._modules:
+                m.set_processor(AttnProcessor2_0())
         if cfg["text_time"]:
             self.add_embedding.linear_1.in_features = cfg["projection_class_embeddings_input_dim"]
         ch = tuple(cfg["block_out_channels"])
@@ -283,16 +309,66 @@ class _UNetBase(nn.Module):
         """Pre-packs the weights on first use (after .to(device) / load_state_dict)."""
         self._need_lib()
         if self._engine is None:
-            self._engine = UNetEngine(self._cfg, self.state_dict(), self.KIND, device=self.device)
+            self._engine = UNetEngine(self._cfg, self.state_dict(), self.KIND, device=self.device,
+                                      ip_scales=self._ip_scales())
         return self._engine
 
     def _apply(self, fn, *a, **k):
         self._engine = None      # weights moved / cast: re-pack lazily
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
+    # ---- seam B3: the attention-processor protocol (src/unet_hacked_tryon.py:793-852) -------------------------------
+    @property
+    def attn_processors(self):
+        """{"<attention module path>.processor": processor} for every Attention layer (src/unet_hacked_tryon.py:793-816)."""
+        return {f"{name}.processor": m.get_processor() for name, m in self.named_modules() if isinstance(m, Attention)}
+
+    def set_attn_processor(self, processor, _remove_lora=False):
+        """src/unet_hacked_tryon.py:818-852: one processor for all layers, or a dict keyed like `attn_processors`.
+        The fused engine implements the semantics of `AttnProcessor2_0` (self-attention; garment cross-attention) and
+        `IPAttnProcessor2_0` (try-on cross-attention) of this package, so only those classes are accepted per slot;
+        IP weights (`to_k_ip`, `to_v_ip`), `scale` and `num_tokens` are taken from the installed processors."""
+        layers = {f"{name}.processor": m for name, m in self.named_modules() if isinstance(m, Attention)}
+        count = len(layers)
+        if isinstance(processor, dict) and len(processor) != count:
+            raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} does not match the"
+                             f" number of attention layers: {count}. Please make sure to pass {count} processor classes.")
+        ip = self._cfg["ip_tokens"] if self.KIND == "tryon" else 0
+        todo = {}
+        for name, attn in layers.items():
+            proc = processor.pop(name) if isinstance(processor, dict) else processor
+            want = IPAttnProcessor2_0 if (ip and name.endswith("attn2.processor")) else AttnProcessor2_0
+            if type(proc) is not want:
+                raise TypeError(f"{name}: the B200 engine fuses {want.__name__} here (got {type(proc).__name__}); other "
+                                "processors have no kernel and there is no PyTorch fallback")
+            if want is IPAttnProcessor2_0:
+                exp = (attn.to_q.weight.shape[0], attn.to_k.weight.shape[1])
+                if tuple(proc.to_k_ip.weight.shape) != exp or tuple(proc.to_v_ip.weight.shape) != exp:
+                    raise ValueError(f"{name}: to_k_ip / to_v_ip must be {exp}, got {tuple(proc.to_k_ip.weight.shape)}")
+                if proc.num_tokens != ip:
+                    raise ValueError(f"{name}: num_tokens {proc.num_tokens} != {ip} image tokens of this UNet")
+            todo[name] = (attn, proc)
+        for attn, proc in todo.values():
+            attn.set_processor(proc, _remove_lora=_remove_lora)
         self._engine = None
-        return super().load_state_dict(*a, **k)
+
+    def _ip_scales(self):
+        return {name[:-len(".attn2.processor")]: float(p.scale) for name, p in self.attn_processors.items()
+                if isinstance(p, IPAttnProcessor2_0)}
+
+    # Checkpoint keys the reference modules own but this UNet never executes. GarmentNet is the SDXL-base UNet built
+    # WITH addition_embed_type="text_time" (train_xl.py:323-325 only nulls the config afterwards), so its checkpoint
+    # carries add_embedding.linear_{1,2}.*, which the garment forward never reads (src/unet_hacked_garmnet.py).
+    IGNORED_CHECKPOINT_PREFIXES = ()
+
+    def load_state_dict(self, state_dict, strict=True, **k):
+        self._engine = None
+        drop = [key for key in state_dict if key.startswith(self.IGNORED_CHECKPOINT_PREFIXES)] \
+            if self.IGNORED_CHECKPOINT_PREFIXES else []
+        if drop:
+            own = set(self.state_dict().keys())
+            state_dict = {key: v for key, v in state_dict.items() if key in own or key not in drop}
+        return super().load_state_dict(state_dict, strict=strict, **k)
 
     def _t_dev(self, timestep):
         if torch.is_tensor(timestep):
@@ -346,6 +422,7 @@ class UNet2DConditionModel(_UNetBase):
 class UNet2DConditionModelGarment(_UNetBase):
     """Garment UNet ("GarmentNet", src/unet_hacked_garmnet.py): exports the post-norm1 activation of every block."""
     KIND = "garment"
+    IGNORED_CHECKPOINT_PREFIXES = ("add_embedding.",)
 
     def __init__(self, cfg=None, state_dict=None, device="cpu", dtype=torch.float16):
         super().__init__(cfg or SDXL_GARMENT, state_dict, device, dtype)

@@ -194,7 +194,10 @@ class DiagonalGaussianDistribution:
         self.std = torch.exp(0.5 * self.logvar)
 
     def sample(self, generator=None):
-        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        # diffusers' randn_tensor: a CPU generator draws on the CPU and the sample is moved to the latents' device
+        dev = self.mean.device
+        rand_dev = "cpu" if (generator is not None and generator.device.type == "cpu" and dev.type != "cpu") else dev
+        noise = torch.randn(self.mean.shape, generator=generator, device=rand_dev, dtype=self.mean.dtype).to(dev)
         return self.mean + self.std * noise
 
     def mode(self):

@@ -29,17 +29,14 @@ const char* b200vton_last_error(void);
 long long b200vton_launch_count(void);
 /* library options: "gemm_2cta_auto" = 1 (default) lets gemm / conv3x3 pick the 2-CTA persistent kernel for large
  * problems when force_bn == 0; 0 keeps every launch on the 1-CTA kernel. "attention_pingpong" = 1 (default) runs
- * b200vton_attention on the two-tile ping-pong kernel when Nq >= 256; 0 keeps the one-tile kernel.
- * "attention_fp16_exp" = 1 (default) selects the ping-pong variant whose softmax evaluates exp2 two elements per SFU
- * op on fp16 arguments and lets the tensor core accumulate the row sums; 0 selects the fp32-softmax variant.
- * "attention_p_in_tmem" = 2 (default) selects the decoupled P-in-TMEM kernel (fp32 softmax, S issued one tile ahead);
- * ("attention_q_tiles" = 1 | 2 pins its query tiles per CTA, 0 = chosen from the K/V length; "attention_poly_exp" =
- * 0 | 1 | 2 of every 4 exponentials evaluated by an FMA-pipe polynomial instead of the SFU, default 0: measured slower);
- * 1 the packed-half kernel with P aliased onto its S columns; with 0,
- * "attention_16_warps" = 1 picks the shared-memory-P variant with 16 softmax warps per CTA, 0 the 8-warp one.
+ * b200vton_attention on the pipelined kernel (attn6.cu: S issued one tile ahead, P in tensor memory) when Nq >= 256;
+ * 0 keeps the one-tile kernel (attn.cu), which the tests use as an independent cross-check.
+ * ("attention_q_tiles" = 1 | 2 pins the pipelined kernel's query tiles per CTA, 0 = chosen from the K/V length;
+ * "attention_poly_exp" = 0 | 1 | 2 of every 4 exponentials evaluated by an FMA-pipe polynomial instead of the SFU,
+ * default 0: measured slower).
  * "gemm_cluster4" = 1 runs large linear layers with 256-wide tiles in four-CTA clusters whose CTA pairs multicast the
  * shared A slabs; 0 (default: it measured slower on B200) keeps two-CTA clusters.
- * "gemm_deep_pipeline" = 1 (EXPERIMENTAL, default 0, not yet run on hardware) gives the 256-wide 2-CTA tiles a sixth
+ * "gemm_deep_pipeline" = 1 (default 0) gives the 256-wide 2-CTA tiles a sixth
  * operand stage in exchange for a one-slot epilogue staging ring.
  * "programmatic_launch" = 1 launches the hot kernels with programmatic stream serialization (their set-up overlaps
  * the previous kernel's tail; they wait for it before allocating tensor memory or touching global memory);

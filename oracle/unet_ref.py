@@ -263,7 +263,7 @@ def attn_self(sd, p, x, heads):
     return F.linear(o, sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"])
 
 
-def attn_cross(sd, p, x, enc, heads, ip_tokens):
+def attn_cross(sd, p, x, enc, heads, ip_tokens, ip_scale=1.0):
     """IPAttnProcessor2_0 (ip_adapter/attention_processor.py:1907-2010) when ip_tokens > 0, else AttnProcessor2_0."""
     q = F.linear(x, sd[f"{p}.to_q.weight"])
     if ip_tokens:
@@ -273,7 +273,7 @@ def attn_cross(sd, p, x, enc, heads, ip_tokens):
     if ip_tokens:
         o_ip = _sdpa(q, F.linear(ip, sd[f"{p}.processor.to_k_ip.weight"]),
                      F.linear(ip, sd[f"{p}.processor.to_v_ip.weight"]), heads)
-        o = o + 1.0 * o_ip
+        o = o + ip_scale * o_ip                                       # :1995, self.scale (1.0 at inference)
     return F.linear(o, sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"])
 
 
@@ -288,7 +288,7 @@ def feed_forward(sd, p, x):
 # ------------------------------------------------------------------------------------------------
 # in-repo logic
 # ------------------------------------------------------------------------------------------------
-def transformer_block(sd, p, x, enc, heads, ip_tokens, garment_features, idx, collect):
+def transformer_block(sd, p, x, enc, heads, ip_tokens, garment_features, idx, collect, ip_scale=1.0):
     """BasicTransformerBlock.forward. collect=None: try-on variant (consume garment_features[idx]);
     collect=list: garment variant (append norm1 output)."""
     n1 = F.layer_norm(x, (x.shape[-1],), sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], 1e-5)
@@ -302,13 +302,13 @@ def transformer_block(sd, p, x, enc, heads, ip_tokens, garment_features, idx, co
         a = attn_self(sd, f"{p}.attn1", mod, heads)
         x = a[:, :x.shape[-2], :] + x                        # :348
     n2 = F.layer_norm(x, (x.shape[-1],), sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], 1e-5)
-    x = attn_cross(sd, f"{p}.attn2", n2, enc, heads, ip_tokens) + x
+    x = attn_cross(sd, f"{p}.attn2", n2, enc, heads, ip_tokens, ip_scale) + x
     n3 = F.layer_norm(x, (x.shape[-1],), sd[f"{p}.norm3.weight"], sd[f"{p}.norm3.bias"], 1e-5)
     x = feed_forward(sd, f"{p}.ff", n3) + x
     return x, idx
 
 
-def transformer_2d(sd, p, x, enc, heads, layers, ip_tokens, garment_features, idx, collect):
+def transformer_2d(sd, p, x, enc, heads, layers, ip_tokens, garment_features, idx, collect, ip_scale=1.0):
     """Transformer2DModel.forward, continuous input, use_linear_projection=True."""
     b, c, hh, ww = x.shape
     res = x
@@ -317,7 +317,7 @@ def transformer_2d(sd, p, x, enc, heads, layers, ip_tokens, garment_features, id
     h = F.linear(h, sd[f"{p}.proj_in.weight"], sd[f"{p}.proj_in.bias"])
     for k in range(layers):
         h, idx = transformer_block(sd, f"{p}.transformer_blocks.{k}", h, enc, heads, ip_tokens, garment_features, idx,
-                                   collect)
+                                   collect, ip_scale)
     h = F.linear(h, sd[f"{p}.proj_out.weight"], sd[f"{p}.proj_out.bias"])
     h = h.reshape(b, hh, ww, c).permute(0, 3, 1, 2).contiguous()
     return h + res, idx
@@ -346,6 +346,7 @@ def _trunk(sd, cfg, sample, emb, enc, garment_features, collect, stop_after_up):
     tl = cfg["transformer_layers_per_block"]
     nh = cfg["num_heads"]
     ip = cfg["ip_tokens"]
+    ips = cfg.get("ip_scale", 1.0)      # IPAttnProcessor2_0.scale of every block (1.0 unless a test installs others)
     idx = 0
     x = F.conv2d(sample, sd["conv_in.weight"], sd["conv_in.bias"], padding=1)
     skips = [x]
@@ -354,13 +355,14 @@ def _trunk(sd, cfg, sample, emb, enc, garment_features, collect, stop_after_up):
             x = resnet_block(sd, f"down_blocks.{i}.resnets.{j}", x, emb)
             if i > 0:
                 x, idx = transformer_2d(sd, f"down_blocks.{i}.attentions.{j}", x, enc, nh[i], tl[i], ip,
-                                        garment_features, idx, collect)
+                                        garment_features, idx, collect, ips)
             skips.append(x)
         if i < len(ch) - 1:
             x = downsample(sd, f"down_blocks.{i}.downsamplers.0", x)
             skips.append(x)
     x = resnet_block(sd, "mid_block.resnets.0", x, emb)
-    x, idx = transformer_2d(sd, "mid_block.attentions.0", x, enc, nh[-1], tl[-1], ip, garment_features, idx, collect)
+    x, idx = transformer_2d(sd, "mid_block.attentions.0", x, enc, nh[-1], tl[-1], ip, garment_features, idx, collect,
+                            ips)
     x = resnet_block(sd, "mid_block.resnets.1", x, emb)
     rnh, rtl = list(reversed(nh)), list(reversed(tl))
     for i in range(len(ch)):
@@ -371,7 +373,7 @@ def _trunk(sd, cfg, sample, emb, enc, garment_features, collect, stop_after_up):
             x = resnet_block(sd, f"up_blocks.{i}.resnets.{j}", x, emb)
             if i < len(ch) - 1:
                 x, idx = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", x, enc, rnh[i], rtl[i], ip,
-                                        garment_features, idx, collect)
+                                        garment_features, idx, collect, ips)
         if i < len(ch) - 1:
             x = upsample(sd, f"up_blocks.{i}.upsamplers.0", x)
     return x

@@ -78,7 +78,7 @@ def test_param_inventory_matches_oracle_and_reference_counts():
     for prod, ora in ((U.SDXL_TRYON, R.SDXL_TRYON), (U.SDXL_GARMENT, R.SDXL_GARMENT),
                       (R.tiny_config("tryon"), R.tiny_config("tryon"))):
         a, b = U.param_shapes(prod), R.unet_param_shapes(ora)
-        assert list(a.keys()).sort() == list(b.keys()).sort()
+        assert sorted(a.keys()) == sorted(b.keys())
         assert all(tuple(a[k]) == tuple(b[k]) for k in a)
     n_t = sum(math.prod(s) for s in U.param_shapes(U.SDXL_TRYON).values())
     n_g = sum(math.prod(s) for s in U.param_shapes(U.SDXL_GARMENT).values())
@@ -87,6 +87,123 @@ def test_param_inventory_matches_oracle_and_reference_counts():
     assert n_g == 2_567_463_684 - 5_245_440
     assert 2.98e9 < n_t < 3.0e9
     assert len([k for k in U.param_shapes(U.SDXL_TRYON) if k.endswith("attn2.processor.to_k_ip.weight")]) == 70
+
+
+def test_loop_oracle_pinned_by_reference_pipeline():
+    """oracle/loop_ref.py (denoise_loop + DDPMRef) against the latents the REFERENCE pipeline produced
+    (tests/golden/pipeline_call_ref.pt, made by oracle/make_golden_pipeline.py from src/tryon_pipeline.py itself): the loop
+    oracle is pinned, not merely self-consistent. Also pins both schedulers' timestep lists and the host-side step()."""
+    from idm_vton_b200.scheduler import DDPMScheduler
+    from oracle import loop_ref as LR
+    from oracle import unet_ref as R
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "pipeline_call_ref.pt"))
+    cfg_t, cfg_g = R.tiny_config("tryon"), R.tiny_config("garment")
+    sd_t = {k: v.half().float() for k, v in R.make_state_dict(cfg_t, seed=11).items()}
+    sd_g = {k: v.half().float() for k, v in R.make_state_dict(cfg_g, seed=22).items()}
+    steps = len(g["latents_per_step"])
+    assert LR.DDPMRef().set_timesteps(steps).tolist() == g["timesteps"].tolist()
+    s = DDPMScheduler()
+    s.set_timesteps(steps)
+    assert s.timesteps.tolist() == g["timesteps"].tolist()
+    with torch.no_grad():
+        for n in range(1, steps + 1):
+            lat = LR.denoise_loop(sd_t, cfg_t, sd_g, cfg_g, g["loop_inputs"], steps, guidance_scale=2.0,
+                                  noises=g["noises"], max_steps=n)
+            ref = g["latents_per_step"][n - 1]
+            assert (lat - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    assert g["n_features"] == 17 and g["loop_inputs"]["mask"].shape[0] == 2 * g["loop_inputs"]["latents"].shape[0]
+
+
+def test_garment_unet_ingests_sdxl_base_checkpoint_keys():
+    """GarmentNet's checkpoint is the SDXL-base UNet (train_xl.py:323-325 nulls addition_embed_type only after
+    construction), so it carries add_embedding.* which the garment forward never reads. strict loading must accept the full
+    key set (and still reject keys that are neither used nor known-dead)."""
+    from idm_vton_b200 import unet as U
+    from oracle import unet_ref as R
+    cfg = R.tiny_config("garment")
+    sd = R.make_state_dict(cfg, seed=2)
+    temb = cfg["block_out_channels"][0] * 4
+    full = dict(sd)
+    full.update({"add_embedding.linear_1.weight": torch.zeros(temb, cfg["projection_class_embeddings_input_dim"]),
+                 "add_embedding.linear_1.bias": torch.zeros(temb), "add_embedding.linear_2.weight": torch.zeros(temb, temb),
+                 "add_embedding.linear_2.bias": torch.zeros(temb)})
+    net = U.UNet2DConditionModelGarment(cfg, dtype=torch.float32)
+    res = net.load_state_dict(full, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(net.state_dict()["conv_in.weight"], sd["conv_in.weight"])
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        net.load_state_dict(dict(full, **{"controlnet_cond.weight": torch.zeros(1)}), strict=True)
+    tnet = U.UNet2DConditionModel(R.tiny_config("tryon"), dtype=torch.float32)        # the try-on UNet uses add_embedding
+    assert "add_embedding.linear_1.weight" in tnet.state_dict()
+
+
+def test_generic_scheduler_interface():
+    """the denoiser derives its per-step coefficients from the generic DDPM interface (alphas_cumprod,
+    config, num_inference_steps), so the caller's own scheduler object works; unsupported configs raise."""
+    from idm_vton_b200.denoise import ddpm_step_coefficients
+    from idm_vton_b200.scheduler import DDPMScheduler
+    for kw in ({}, {"rescale_betas_zero_snr": True}):
+        s = DDPMScheduler(**kw)
+        s.set_timesteps(30)
+        assert all(ddpm_step_coefficients(s, int(t)) == s.step_coefficients(int(t)) for t in s.timesteps)
+
+    class Foreign:          # what a diffusers DDPMScheduler exposes (no step_coefficients / previous_timestep)
+        def __init__(self, **over):
+            self.alphas_cumprod = DDPMScheduler().alphas_cumprod
+            self.config = dict(num_train_timesteps=1000, prediction_type="epsilon", variance_type="fixed_small",
+                               clip_sample=False, **over)
+            self.num_inference_steps = 30
+
+    s = DDPMScheduler()
+    s.set_timesteps(30)
+    assert ddpm_step_coefficients(Foreign(), 967) == s.step_coefficients(967)
+    with pytest.raises(NotImplementedError):
+        ddpm_step_coefficients(Foreign(thresholding=True), 967)
+    with pytest.raises(TypeError):
+        ddpm_step_coefficients(object(), 967)
+
+
+def test_attention_processor_seam_structure():
+    """Seam B3 on the host: every Attention layer exposes a processor under the reference's names
+    (src/unet_hacked_tryon.py:793-852), IP weights live in `...attn2.processor.to_{k,v}_ip.weight`
+    (ip_adapter/attention_processor.py:1904-1905), set_attn_processor validates like the reference, and the processors
+    refuse CPU tensors instead of falling back to PyTorch."""
+    from idm_vton_b200 import unet as U
+    from idm_vton_b200.attention_processor import Attention, AttnProcessor2_0, IPAttnProcessor2_0
+    from oracle import unet_ref as R
+    cfg_t, cfg_g = R.tiny_config("tryon"), R.tiny_config("garment")
+    net = U.UNet2DConditionModel(cfg_t, R.make_state_dict(cfg_t, seed=1), dtype=torch.float32)
+    gar = U.UNet2DConditionModelGarment(cfg_g, R.make_state_dict(cfg_g, seed=2), dtype=torch.float32)
+    procs = net.attn_processors
+    n_blocks = 17
+    assert len(procs) == 2 * n_blocks and len(gar.attn_processors) == 2 * n_blocks
+    assert all(k.endswith(".attn1.processor") or k.endswith(".attn2.processor") for k in procs)
+    assert all(type(p) is (IPAttnProcessor2_0 if k.endswith("attn2.processor") else AttnProcessor2_0) for k, p in procs.items())
+    assert all(type(p) is AttnProcessor2_0 for p in gar.attn_processors.values())
+    assert sorted(net.state_dict()) == sorted(R.unet_param_shapes(cfg_t))       # registering processors adds no keys
+    k0 = "down_blocks.1.attentions.0.transformer_blocks.0.attn2.processor"
+    assert procs[k0].num_tokens == 16 and procs[k0].scale == 1.0
+    assert procs[k0].to_k_ip.weight is net.state_dict(keep_vars=True)[k0 + ".to_k_ip.weight"]
+    attn = dict(net.named_modules())[k0[:-len(".processor")]]
+    assert isinstance(attn, Attention) and attn.heads == 2 and attn.to_out[0].bias is not None
+    # reference error for a dict of the wrong size (src/unet_hacked_tryon.py:833-837)
+    with pytest.raises(ValueError, match="does not match the number of attention layers: 34"):
+        net.set_attn_processor({k0: procs[k0]})
+    with pytest.raises(TypeError, match="IPAttnProcessor2_0"):
+        net.set_attn_processor(AttnProcessor2_0())
+    bad = {k: (IPAttnProcessor2_0(128, 256, num_tokens=4) if k == k0 else p) for k, p in procs.items()}
+    with pytest.raises(ValueError, match="num_tokens"):
+        net.set_attn_processor(bad)
+    new = {k: (IPAttnProcessor2_0(p.hidden_size, p.cross_attention_dim, scale=0.25, num_tokens=16)
+               if isinstance(p, IPAttnProcessor2_0) else AttnProcessor2_0()) for k, p in procs.items()}
+    net.set_attn_processor(dict(new))
+    assert net.attn_processors[k0] is new[k0] and net._ip_scales()[k0[:-len(".attn2.processor")]] == 0.25
+    assert net.state_dict(keep_vars=True)[k0 + ".to_v_ip.weight"] is new[k0].to_v_ip.weight
+    gar.set_attn_processor(AttnProcessor2_0())          # one processor for all layers
+    # no CPU / PyTorch fallback behind the protocol
+    a = Attention(query_dim=128, heads=2)
+    with pytest.raises(RuntimeError, match="no PyTorch fallback"):
+        a(torch.zeros(1, 8, 128))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -103,7 +220,7 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(so, name), f"{name} declared in include/b200vton.h but not exported"
     assert set(lib.SIGNATURES) <= set(declared)
     l = lib.load()
-    assert l.b200vton_version() == 100
+    assert l.b200vton_version() == lib.ABI_VERSION
     # argument validation happens before any CUDA work: invalid shapes return an error code + message, no crash
     rc = l.b200vton_gemm_f16(None, 8, None, 8, None, 8, 16, 16, 60, None, None, 0, None, 0, 0, 0, 0, None)
     assert rc == 1 and b"multiple of 64" in l.b200vton_last_error()
@@ -316,11 +433,10 @@ def test_library_options_and_argument_checks_without_gpu():
     header = open(os.path.join(ROOT, "include", "b200vton.h")).read()
     block = header[header.index("/* library options:"):header.index("int b200vton_set_option")]
     names = sorted(set(re.findall(r'"([a-z0-9_]+)"', block)))
-    assert {"gemm_2cta_auto", "gemm_cluster4", "programmatic_launch", "attention_p_in_tmem", "attention_q_tiles",
+    assert {"gemm_2cta_auto", "gemm_cluster4", "programmatic_launch", "attention_pingpong", "attention_q_tiles",
             "attention_poly_exp"} <= set(names)
     defaults = {"gemm_2cta_auto": 1, "gemm_cluster4": 0, "gemm_deep_pipeline": 0, "programmatic_launch": 0, "attention_pingpong": 1,
-                "attention_fp16_exp": 1, "attention_p_in_tmem": 2, "attention_q_tiles": 0, "attention_poly_exp": 0,
-                "attention_16_warps": 1}
+                "attention_q_tiles": 0, "attention_poly_exp": 0}
     for n in names:
         assert n in defaults, f"option {n} documented in the header but not covered here"
         assert l.b200vton_set_option(n.encode(), defaults[n]) == 0

@@ -397,50 +397,10 @@ def test_attention_per_step_kv_base(lib):
         close(out[:Bp], ref_u, tol=3e-3)
 
 
-def test_attention_fp16_exp_vs_fp32_softmax(lib):
-    """The packed-half softmax kernel (attn3.cu) against the fp32-softmax ping-pong kernel (attn2.cu) and the fp32
-    reference, on a diffuse and on a peaky score distribution."""
-    B, H, N = 2, 4, 1024
-    C = H * 64
-    for qscale in (1.0, 4.0):
-        q, k, v = rnd(B, N, C, scale=qscale, seed=1), rnd(B, N, C, seed=2), rnd(B, N, C, seed=3)
-        ref = _attn_ref(q, k, v, H, 0.125)
-        lib.set_option("attention_p_in_tmem", 0)
-        try:
-            o3 = lib.attention(q, k, v, heads=H)
-            lib.set_option("attention_fp16_exp", 0)
-            o2 = lib.attention(q, k, v, heads=H)
-        finally:
-            lib.set_option("attention_fp16_exp", 1)
-            lib.set_option("attention_p_in_tmem", 2)
-        e3, e2 = close(o3, ref, tol=4e-3), close(o2, ref, tol=4e-3)
-        print(f"qscale {qscale}: fp16-exp err {e3:.2e}, fp32-softmax err {e2:.2e}")
-
-
-def test_attention_16_warp_variant_matches_8_warp(lib):
-    """attn4.cu (16 softmax warps, column-split rows, smem max exchange) vs attn3.cu on the try-on attn1 pattern."""
-    Bp, H, N, Ng = 2, 5, 640, 1000
-    C = H * 64
-    qkv = rnd(2 * Bp, N, 3 * C, seed=11)
-    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-    gkv = rnd(Bp, Ng, 2 * C, seed=12)
-    lib.set_option("attention_p_in_tmem", 0)
-    try:
-        o16 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
-        lib.set_option("attention_16_warps", 0)
-        o8 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
-    finally:
-        lib.set_option("attention_16_warps", 1)
-        lib.set_option("attention_p_in_tmem", 2)
-    ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
-    close(o16[Bp:], ref_c, tol=3e-3)
-    close(o16, o8, tol=2e-3)
-
-
 def test_attention_p_in_tmem_variant(lib):
-    """attn6.cu (default: P in its own tensor-memory columns, S issued one tile ahead, fp32 softmax) and attn5.cu (P
-    aliased onto S, packed-half softmax) vs attn3.cu (P through shared memory) and the fp32 reference: two segments
-    with ragged tails, the zero-KV half, the accumulate mode and a peaky distribution."""
+    """attn6.cu (P in its own tensor-memory columns, S issued one tile ahead, fp32 softmax) vs the one-tile kernel of
+    attn.cu (option attention_pingpong=0) and the fp32 reference: two segments with ragged tails, the zero-KV half, the
+    accumulate mode and a peaky distribution."""
     Bp, H, N, Ng = 2, 5, 640, 1000
     C = H * 64
     qkv = rnd(2 * Bp, N, 3 * C, seed=21)
@@ -448,15 +408,10 @@ def test_attention_p_in_tmem_variant(lib):
     gkv = rnd(Bp, Ng, 2 * C, seed=22)
     o5 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
     try:
-        lib.set_option("attention_p_in_tmem", 1)
-        o5b = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
-        lib.set_option("attention_p_in_tmem", 0)
-        lib.set_option("attention_16_warps", 0)
+        lib.set_option("attention_pingpong", 0)
         o3 = lib.attention(q, k, v, gkv[..., :C], gkv[..., C:], kv1_off=Bp, heads=H)
     finally:
-        lib.set_option("attention_16_warps", 1)
-        lib.set_option("attention_p_in_tmem", 2)
-    close(o5b, o3, tol=2e-3)
+        lib.set_option("attention_pingpong", 1)
     ref_c = _attn_ref(q[Bp:], torch.cat([k[Bp:], gkv[..., :C]], 1), torch.cat([v[Bp:], gkv[..., C:]], 1), H, 0.125)
     ref_u = _attn_ref(q[:Bp], k[:Bp], v[:Bp], H, 0.125, n_zero=Ng)
     close(o5[Bp:], ref_c, tol=3e-3)
