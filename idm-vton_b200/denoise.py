@@ -48,8 +48,12 @@ def ddpm_step_coefficients(scheduler, t):
 
 
 class TryOnDenoiser:
-    def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=8):
-        """hoist_garment: the garment UNet depends on the timestep but not on the latents, so all
+    def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=8, max_kv_bytes=None):
+        """max_kv_bytes: budget for the resident garment K/V of the hoisted passes (default: 60% of the free device memory
+        when the step tables are set). When all denoise steps do not fit (e.g. 1024x1024, 50 steps, batch 4 = 84 GB),
+        the steps are hoisted window by window: K/V of `window` consecutive steps are resident at a time and the next
+        window's garment passes run when the loop reaches it — same arithmetic, same graph.
+        hoist_garment: the garment UNet depends on the timestep but not on the latents, so all
         its passes are run BEFORE the loop, batched over `garment_chunk` timesteps at a time (large-M GEMMs, weights
         read once per chunk instead of once per step), and the garment K/V of every try-on block are projected once
         for all steps; the per-step graph then contains the try-on UNet only and walks the K/V by a device-side
@@ -61,7 +65,10 @@ class TryOnDenoiser:
         self._graph = None
         self.hoist_garment = hoist_garment
         self.garment_chunk = garment_chunk
+        self.max_kv_bytes = max_kv_bytes
         self.gkv_all = None
+        self.window = None
+        self.win_start = -1
 
     # -------------------------------------------------------------------------------------------
     def prepare(self, latents, mask, masked_image_latents, pose_latents, cloth_latents, prompt_embeds,
@@ -114,35 +121,59 @@ class TryOnDenoiser:
             rows.append([self.guidance_scale, *ddpm_step_coefficients(scheduler, int(t))])
         self.coef_table = torch.tensor(rows, dtype=torch.float32, device=self.device)
         self.t_table = torch.tensor([float(int(t)) for t in timesteps], dtype=torch.float32, device=self.device)
-        self.base_table = torch.arange(len(rows), dtype=torch.int32, device=self.device) * self.Bg
+        T = len(rows)
+        self.window = T
         if self.hoist_garment:
-            self.precompute_garment()
+            budget = self.max_kv_bytes
+            if budget is None:
+                free, _ = torch.cuda.mem_get_info(self.device)
+                held = sum(g.numel() * 2 for g in self.gkv_all) if self.gkv_all is not None else 0
+                budget = int(0.6 * (free + held))
+            per_step = self.kv_bytes_per_step()
+            if per_step * T > budget:
+                w = max(1, budget // per_step)
+                self.window = max(self.garment_chunk, w // self.garment_chunk * self.garment_chunk) if w >= self.garment_chunk else w
+        self.base_table = (torch.arange(T, dtype=torch.int32, device=self.device) % self.window) * self.Bg
+        if self.hoist_garment:
+            self.precompute_garment(0)
 
-    def precompute_garment(self):
-        """All garment-UNet passes of the request (one per timestep), batched, then the garment K/V projection of every
-        try-on block for all timesteps: gkv_all[i] = [T*Bg, Ng, 2C] in timestep-major order."""
+    def kv_bytes_per_step(self):
+        """Bytes of garment K/V one denoise step keeps resident: sum over the try-on blocks of Bg * Ng * 2C fp16."""
+        ch = self.tryon.ch
+        n, lvl_tokens = (self.h, self.w), {}
+        for lvl, c in enumerate(ch):
+            lvl_tokens[c] = n[0] * n[1]
+            n = ((n[0] - 1) // 2 + 1, (n[1] - 1) // 2 + 1)
+        return sum(self.Bg * lvl_tokens[b.c] * 2 * b.c * 2 for b in self.tryon.blocks())
+
+    def precompute_garment(self, win_start=0):
+        """The garment-UNet passes of the steps [win_start, win_start + window) of the request (one per timestep), batched,
+        then the garment K/V projection of every try-on block for those timesteps: gkv_all[i] = [window*Bg, Ng, 2C] in
+        timestep-major order (window = all steps unless the K/V budget forces several windows)."""
         L = self.L
-        T, Bg = self.t_table.numel(), self.Bg
+        T_all, Bg = self.t_table.numel(), self.Bg
+        T = min(self.window, T_all - win_start)
         blocks = self.tryon.blocks()
         gkv = self.gkv_all            # buffers of an earlier same-shaped request are overwritten in place
-        if gkv is not None and gkv[0].shape[0] != T * Bg:
+        if gkv is not None and gkv[0].shape[0] != min(self.window, T_all) * Bg:
             gkv = None
             self._graph = None
         self.gkv_all = None
         for c0 in range(0, T, self.garment_chunk):
             n = min(self.garment_chunk, T - c0)
-            t_rows = self.t_table[c0:c0 + n].repeat_interleave(Bg).contiguous()            # timestep-major rows
+            t_rows = self.t_table[win_start + c0:win_start + c0 + n].repeat_interleave(Bg).contiguous()   # timestep-major rows
             x_big = self.x_g.repeat(n, 1, 1, 1)
             ctx_big = [(kv_t.repeat(n, 1, 1), None) for kv_t, _ in self.ctx_g]
             feats = []
             self.garment.forward(x_big, self.garment.time_embedding(t_rows, n * Bg), ctx_big, collect=feats)
             if gkv is None:
-                gkv = [torch.empty((T * Bg, f.shape[1], 2 * f.shape[2]), dtype=torch.float16, device=self.device)
-                       for f in feats]
+                gkv = [torch.empty((min(self.window, T_all) * Bg, f.shape[1], 2 * f.shape[2]), dtype=torch.float16,
+                                   device=self.device) for f in feats]
             for i, (blk, f) in enumerate(zip(blocks, feats)):
                 self.tryon.garment_kv(blk, f, out=gkv[i][c0 * Bg:(c0 + n) * Bg])
             del feats, x_big, ctx_big
         self.gkv_all = gkv
+        self.win_start = win_start
 
     # -------------------------------------------------------------------------------------------
     def _launch_step(self):
@@ -179,6 +210,8 @@ class TryOnDenoiser:
 
     def step(self, i, noise=None, use_graph=True):
         """Runs denoise step i (tables from set_step_tables). noise: [B,4,h,w] fp16 variance noise or None."""
+        if self.hoist_garment and self.gkv_all is not None and (i // self.window) * self.window != self.win_start:
+            self.precompute_garment((i // self.window) * self.window)      # next K/V window (budgeted hoisting)
         self.t_dev.copy_(self.t_table[i:i + 1])
         self.coef.copy_(self.coef_table[i])
         self.step_base.copy_(self.base_table[i:i + 1])

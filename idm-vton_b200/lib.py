@@ -218,7 +218,7 @@ _gn32_ws = {}
 
 
 def groupnorm_f32_nhwc(x, gamma, beta, eps, silu):
-    """x: logical [B,C,H,W] fp32 in channels_last memory (= dense NHWC); returns the same layout. EXPERIMENTAL."""
+    """x: logical [B,C,H,W] fp32 in channels_last memory (= dense NHWC); returns the same layout."""
     lib = load()
     B, C, H, W = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)

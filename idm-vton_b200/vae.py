@@ -23,9 +23,12 @@ import torch.nn.functional as F
 # 805 MB tensors, and feeding an NHWC kernel from torch's NCHW GroupNorm adds two layout copies per convolution. The
 # switch therefore stays off until those passes have NHWC kernels of their own (B200VTON_VAE_TF32_CONV=1 to enable).
 _ENGINE_CONV = os.environ.get("B200VTON_VAE_TF32_CONV", "0") == "1"
-# EXPERIMENTAL (written at the end of round 1, not yet run on hardware): keep the whole VAE in NHWC (channels_last) so
-# that the engine convolution needs no layout copies, with GroupNorm(+SiLU) on `b200vton_groupnorm_nhwc_f32`.
-_ENGINE_NHWC = os.environ.get("B200VTON_VAE_NHWC", "0") == "1"
+# The whole fp32 VAE in NHWC (channels_last): the engine convolution then needs no layout copies and GroupNorm(+SiLU) runs on
+# `b200vton_groupnorm_nhwc_f32`. Validated on B200 in round 2 (tests -k "fp32_nhwc or vae_nhwc"; profiles/r2_vae_nhwc.json):
+# encode 62.5 -> 30.1 ms, decode 106.5 -> 50.6 ms per 2 images at 1024x768 (fp16 cuDNN: 46 / 82 ms). Default ON
+# (B200VTON_VAE_NHWC=0 restores the cuDNN NCHW route); fp32 data, TF32 products — the arithmetic class the reference's
+# fp32 VAE gets from cuDNN under torch's default `cudnn.allow_tf32`.
+_ENGINE_NHWC = os.environ.get("B200VTON_VAE_NHWC", "1") == "1"
 
 
 def _use_nhwc(x):

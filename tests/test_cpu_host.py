@@ -316,6 +316,15 @@ def _gloo_worker(rank, world, port, out):
     sd = {f"w{i}": (torch.randn(7 + i, 5, generator=g) if rank == 0 else torch.zeros(7 + i, 5)) for i in range(6)}
     sd["h"] = torch.randn(9, generator=g).half() if rank == 0 else torch.zeros(9).half()
     broadcast_state_dict(sd, src=0, bucket_bytes=200)
+    # the path bench.py uses: one flat arena per UNet, views as the state dict, broadcast in place in buckets
+    from idm_vton_b200.parallel import alloc_state_dict_arena, broadcast_arena
+    shapes = {"a": (3, 5), "b": (130,), "c": (2, 2, 2)}
+    views, flat = alloc_state_dict_arena(shapes, torch.float32, "cpu", align=8)
+    assert all(v.data_ptr() % 32 == 0 and tuple(v.shape) == shapes[k] for k, v in views.items())
+    for k, v in views.items():
+        v.copy_(torch.randn(shapes[k], generator=g) if rank == 0 else torch.zeros(shapes[k]))
+    broadcast_arena(flat, src=0, bucket_bytes=64)
+    sd.update({f"arena_{k}": v for k, v in views.items()})
     chk = torch.tensor([sum(v.double().sum().item() for v in sd.values())], dtype=torch.float64)
     dist.all_reduce(chk, op=dist.ReduceOp.MAX)
     mine = list(shard_requests(10, world, rank))
@@ -516,13 +525,14 @@ def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
 
 def test_bench_emits_a_line_when_the_e2e_section_stalls():
     """bench.py's safety net: value / roofline are measured before the e2e section, and if that section does not return
-    within B200VTON_E2E_TIMEOUT the line is still printed (e2e marked unavailable) and the process exits 0."""
+    within B200VTON_E2E_TIMEOUT the line is still printed (e2e marked unavailable) and the process exits NON-ZERO (3): a
+    hang must not surface as rc=0."""
     import json
     import subprocess
     import sys
     probe = os.path.join(ROOT, "tests", "helpers", "bench_guard_probe.py")
     r = subprocess.run([sys.executable, probe], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.returncode == 3, r.stderr[-2000:]
     lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1 and "SHOULD NOT REACH" not in r.stdout
     d = json.loads(lines[0])

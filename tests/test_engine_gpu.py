@@ -207,3 +207,31 @@ def test_hoisted_garment_pass_matches_stepwise(tiny):
     e = _err(outs[1], outs[0])
     print(f"hoisted vs stepwise after 4 steps: {e:.2e}")
     assert e < 3e-3
+
+
+def test_windowed_hoisting_is_bit_identical(tiny):
+    """K/V budget smaller than the whole loop (config 4: 84 GB at 1024^2 / 50 steps / batch 4): the garment passes are
+    hoisted window by window. Same launches per (step, garment), so the latents must be bit-identical to the fully
+    resident schedule, and the captured graph must survive the window switches."""
+    from oracle import loop_ref as LR
+    from idm_vton_b200.denoise import TryOnDenoiser
+    from idm_vton_b200.scheduler import DDPMScheduler
+    B, h, w, steps, run = 2, 16, 16, 30, 7
+    inp = LR.synth_loop_inputs(tiny["cfg_t"], tiny["cfg_g"], B, h, w, seed=31)
+    inp = {k: (v.half().float() if k != "add_time_ids" else v).cuda() for k, v in inp.items()}
+    sch = DDPMScheduler()
+    sch.set_timesteps(steps)
+    outs, windows = [], []
+    for steps_resident in (None, 3):
+        den = TryOnDenoiser(tiny["eng_t"], tiny["eng_g"], garment_chunk=2)
+        den.prepare(**inp)
+        if steps_resident:
+            den.max_kv_bytes = steps_resident * den.kv_bytes_per_step()
+        den.set_step_tables(sch, sch.timesteps)
+        windows.append(den.window)
+        for i in range(run):
+            den.step(i, None, use_graph=True)
+        torch.cuda.synchronize()
+        outs.append(den.latents.clone())
+    assert windows == [steps, 2]          # 3 steps fit -> rounded down to a multiple of the garment chunk (2)
+    assert torch.equal(outs[0], outs[1])

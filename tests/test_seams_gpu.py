@@ -270,3 +270,37 @@ def test_pipeline_call_vs_reference_golden(tiny_modules):
     assert max(errs) < 6e-3
     assert d_img.mean().item() < 5e-3 and d_img.max().item() < 0.1
     # (a wrong RNG order / channel order / batch order is an O(1) error, far outside these gates)
+
+
+def test_pipeline_rebuilds_denoiser_after_weight_reload(tiny_modules):
+    """`pipe.unet.load_state_dict(...)` re-packs the engine lazily; the pipeline must not keep stepping a
+    denoiser (and CUDA graph) that still points at the old packed weights."""
+    from oracle import make_golden_pipeline as MG
+    from oracle import unet_ref as R
+    from idm_vton_b200 import unet as U
+    from idm_vton_b200.pipeline import StableDiffusionXLInpaintPipeline
+    from idm_vton_b200.scheduler import DDPMScheduler
+    dev, f16 = "cuda", torch.float16
+    cfg_t = tiny_modules["cfg_t"]
+    net_t = U.UNet2DConditionModel(cfg_t, tiny_modules["sd_t"]).to(dev, f16)
+    pipe = StableDiffusionXLInpaintPipeline(
+        vae=MG.make_vae().to(dev, f16), text_encoder=None, text_encoder_2=None, tokenizer=None, tokenizer_2=None,
+        unet=net_t, unet_encoder=tiny_modules["net_g"], scheduler=DDPMScheduler(),
+        image_encoder=MG.make_image_encoder(cfg_t["resampler"]["embedding_dim"]).to(dev, f16))
+    inp = {k: (v.to(dev, f16) if k not in ("image", "mask_image") else v.to(dev)) for k, v in MG.make_call_inputs(cfg_t).items()}
+
+    def run():
+        torch.manual_seed(1234)
+        pipe(**MG.call_kwargs(inp, torch.Generator().manual_seed(42)), output_type="pt")
+        return pipe._last_latents.float().cpu()
+
+    a = run()
+    den0 = pipe._denoiser
+    assert torch.equal(a, run()) and pipe._denoiser is den0            # same weights: same denoiser, same result
+    new = {k: v.to(dev, f16) for k, v in R.make_state_dict(cfg_t, seed=77).items()}
+    pipe.unet.load_state_dict(new)
+    b = run()
+    assert pipe._denoiser is not den0 and _err(b, a) > 1e-2            # new weights took effect
+    fresh = U.UNet2DConditionModel(cfg_t, R.make_state_dict(cfg_t, seed=77)).to(dev, f16)
+    pipe.unet = fresh
+    assert torch.equal(run(), b)
