@@ -12,6 +12,19 @@ import torch
 from .engine import CIN_PAD, UNetEngine
 
 
+class nvtx_range:
+    """NVTX range around a host-side stage (visible in nsys / ncu --nvtx; a no-op cost of ~1 us otherwise)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+
+
 def ddpm_step_coefficients(scheduler, t):
     """(sqrt(1-abar_t), 1/sqrt(abar_t), x0 coeff, x_t coeff, sigma_t) of DDPMScheduler.step at timestep t, computed in
     fp32 torch like diffusers does, from the GENERIC scheduler interface only — `alphas_cumprod`,
@@ -77,6 +90,15 @@ class TryOnDenoiser:
         [Bt,4,h,w], prompt_embeds [Bt,77,X], add_text_embeds [Bt,P], add_time_ids [Bt,6], image_embeds [Bt,16,X]
         with Bt = 2B under CFG ([uncond ; cond] order, src/tryon_pipeline.py:1711-1714); cloth_latents [Bg,4,h,w],
         text_embeds_cloth [Bg,77,X]."""
+        torch.cuda.nvtx.range_push("b200vton.prepare(context K/V, aug_emb, static input channels)")
+        try:
+            self._prepare(latents, mask, masked_image_latents, pose_latents, cloth_latents, prompt_embeds, add_text_embeds,
+                          add_time_ids, image_embeds, text_embeds_cloth, guidance_scale, do_cfg)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _prepare(self, latents, mask, masked_image_latents, pose_latents, cloth_latents, prompt_embeds, add_text_embeds,
+                 add_time_ids, image_embeds, text_embeds_cloth, guidance_scale, do_cfg):
         L = self.L
         f16 = torch.float16
         B, _, h, w = latents.shape
@@ -150,6 +172,10 @@ class TryOnDenoiser:
         """The garment-UNet passes of the steps [win_start, win_start + window) of the request (one per timestep), batched,
         then the garment K/V projection of every try-on block for those timesteps: gkv_all[i] = [window*Bg, Ng, 2C] in
         timestep-major order (window = all steps unless the K/V budget forces several windows)."""
+        with nvtx_range(f"b200vton.garment_passes[{win_start}:{win_start + self.window}]"):
+            self._precompute_garment(win_start)
+
+    def _precompute_garment(self, win_start):
         L = self.L
         T_all, Bg = self.t_table.numel(), self.Bg
         T = min(self.window, T_all - win_start)
@@ -219,13 +245,14 @@ class TryOnDenoiser:
             self.noise.copy_(noise)
         else:
             self.noise.zero_()
-        if use_graph:
-            if self._graph is None:
-                self.capture()
-                self.t_dev.copy_(self.t_table[i:i + 1])
-                self.coef.copy_(self.coef_table[i])
-                self.step_base.copy_(self.base_table[i:i + 1])
-            self._graph.replay()
-        else:
-            self._launch_step()
+        with nvtx_range("b200vton.denoise_step"):
+            if use_graph:
+                if self._graph is None:
+                    self.capture()
+                    self.t_dev.copy_(self.t_table[i:i + 1])
+                    self.coef.copy_(self.coef_table[i])
+                    self.step_base.copy_(self.base_table[i:i + 1])
+                self._graph.replay()
+            else:
+                self._launch_step()
         return self.latents

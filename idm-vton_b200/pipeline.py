@@ -73,6 +73,7 @@ class _StageTrace:
 
     def mark(self, name):
         self.ev.append((name, self._rec()))
+        torch.cuda.nvtx.mark(f"b200vton.pipeline:{name}")
 
     def report(self):
         import sys
