@@ -194,13 +194,39 @@ void set_auto_v2(int on) { g_auto_v2 = on; }
 static int g_cluster4 = 0;
 void set_cluster4(int on) { g_cluster4 = on; }
 
-static int pick_bn2(int N, bool geglu) {
-  if (geglu) return N % 256 == 0 ? 256 : 128;
-  if (N % 256 == 0) return 256;
-  if (N % 192 == 0) return 192;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  return N > 192 ? 256 : (N > 160 ? 192 : (N > 128 ? 160 : 128));
+// Tile width of the 2-CTA kernel from a cost model instead of divisibility rules (round 2). Per 64-deep K slab a CTA pair
+// spends max(MMA time, operand-delivery time): the 256 x BN x 64 MMA takes 2*BN clk (8192 dense fp16 FLOP/clk/SM), and each
+// CTA pulls 16 KB of A + 64*BN bytes of W through the L2 -> SM path, whose chip-wide cap is ~6300 B/clk
+// (/opt/skills/guides/B300_MICROARCH.md "LTS throughput cap"; measured here as 40-42 B/clk/SM with all SMs pulling). So
+// narrow tiles are delivery-bound (BN 128: 577 clk per slab for 256 MMA clk) and the cost per output column falls with
+// BN (4.5 / 3.9 / 3.5 / 3.0 clk per column and slab for BN 128 / 160 / 192 / 256). Against that stands quantisation:
+// tiles = ceil(M/256) * ceil(N/BN) run in rounds of 74 clusters. Example the old rule got wrong: N = 640, M = 12288 —
+// BN 160 gives 192 tiles = 3 rounds x 625 clk, BN 256 gives 144 tiles (the third column tile half empty) = 2 rounds x
+// 769 clk: 18% less, which is where cuBLAS was ahead (profiles/r1_microbench_gemm2_final.jsonl: 1124 vs 786 TFLOP/s on
+// [12288 x 640 x 2560]). Cout = 320 at M = 49152 still resolves to 160 (6 rounds either way).
+static int pick_bn2(int N, bool geglu, int m_tiles, bool has_shortcut) {
+  const int m_pairs = cdiv(m_tiles, 2);
+  const int max_clusters = kSMs / 2;
+  const int cands[4] = {256, 192, 160, 128};
+  double best = 1e300;
+  int best_bn = 0;
+  for (int bn : cands) {
+    if (geglu && ((bn != 256 && bn != 128) || N % bn != 0)) continue;
+    if (has_shortcut && bn == 192) continue;   // two accumulators per tile: 2 * 192 columns do not fit a power-of-two alloc
+    const long long tiles = static_cast<long long>(m_pairs) * cdiv(N, bn);
+    const long long clusters = tiles < max_clusters ? tiles : max_clusters;
+    const long long rounds = (tiles + clusters - 1) / clusters;
+    double bw = 6300.0 / (2.0 * clusters);   // B/clk per SM when `clusters` pairs pull at once
+    if (bw > 80.0) bw = 80.0;                // a lone SM does not get the whole crossbar
+    const double mma = 2.0 * bn;
+    const double l2 = (16384.0 + 64.0 * bn) / bw;
+    const double cost = rounds * (mma > l2 ? mma : l2);
+    if (cost < best * 0.999) {               // ties go to the wider tile (fewer bytes per FLOP)
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn ? best_bn : 128;
 }
 
 // Returns the 2-CTA tile width to use, or 0 for the 1-CTA kernel.
@@ -209,10 +235,10 @@ static int choose_v2(int m_tiles, int N, bool geglu, bool has_shortcut, int forc
   if (force_bn >= 1000) {
     bn = force_bn - 1000;
   } else if (force_bn == 0 && g_auto_v2 && m_tiles >= 4 && N >= 128 && !(geglu && N % 128 != 0)) {
-    bn = pick_bn2(N, geglu);
+    bn = pick_bn2(N, geglu, m_tiles, has_shortcut);
   }
   // with a fused shortcut the tile carries two accumulators (one TMEM stage): widths whose pair fits 512 columns
-  if (has_shortcut && bn == 192) bn = (force_bn >= 1000) ? 0 : 160;
+  if (has_shortcut && bn == 192) bn = 0;
   return bn;
 }
 

@@ -28,12 +28,30 @@ __device__ __forceinline__ uint4 gn_load(const GnSrc& s, long long row, int v) {
   return *reinterpret_cast<const uint4*>(s.x1 + row * s.C1 + (c - s.C0));
 }
 
-// Deterministic two-stage statistics (no atomics, so a CUDA-graph replay is bit-identical to eager launches):
-//   stage 1: CTA (chunk, b) reduces its rows -> partial[b][chunk][g] = {sum, sum of squares} (fixed reduction order)
-//   stage 2: the apply kernel's first 32 threads sum the chunk partials of their group in order (double).
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW, int rows_per_cta, double* partial) {
+// ONE launch per GroupNorm (round 2; round 1 ran a statistics kernel and an apply kernel = 3 passes over the tensor):
+//   phase 1: CTA (chunk, b) streams its rows once, accumulates per-channel sums / sums of squares in a fixed order and —
+//            when its rows fit shared memory (RESIDENT) — parks the raw fp16 rows there; it publishes
+//            partial[b][chunk][g] = {sum, sum of squares} (double).
+//   barrier: the CTAs of ONE sample meet at a sense-reversing barrier in global memory (count + sense per sample; the
+//            last arriver resets the count and flips the sense, so the state is reusable by the next launch / graph
+//            replay without host intervention). All CTAs of a launch are co-resident by construction (grid <= SMs x
+//            occupancy, see groupnorm_impl), so the spin cannot starve an unscheduled CTA.
+//   phase 2: every CTA sums the chunk partials of its sample in a FIXED order (no atomics on data: a CUDA-graph replay is
+//            bit-identical to eager launches), derives mean / rstd, and normalises its rows from shared memory (RESIDENT:
+//            the tensor is read from global memory once) or by re-reading them (L2-resident for the UNet's sizes).
+// HBM traffic: 1 read + 1 write of the tensor; 46 launches per try-on step instead of 92.
+struct GnBarrier {
+  int count;
+  int sense;
+};
+
+template <bool RESIDENT>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_fused_kernel(GnSrc src, int HW, int rows_per_cta, double* partial, GnBarrier* bar, const __half* gamma,
+                const __half* beta, float eps, int silu, __half* out) {
   pdl_launch_dependents();
   pdl_wait();
+  extern __shared__ uint4 gn_rows[];   // RESIDENT: [rows_per_cta][V] raw rows of this CTA
   const int C = src.C0 + src.C1;
   const int V = C / 8;
   const int cpg = C / GN_GROUPS;
@@ -43,14 +61,17 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
   const int r_end = min(HW, r_begin + rows_per_cta);
   __shared__ float ps[GN_THREADS * 8];  // [row_lane][C] partial sums
   __shared__ float pq[GN_THREADS * 8];  // [row_lane][C] partial sums of squares
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  __shared__ int s_sense;
   const int v = threadIdx.x % V;
   const int rl = threadIdx.x / V;
+  if (threadIdx.x == 0) s_sense = *reinterpret_cast<volatile int*>(&bar[b].sense);   // read BEFORE anyone can flip it
+  // ---------------- phase 1: statistics (and parking the rows)
   if (rl < row_lanes) {
     float sum[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-    for (int r = r_begin + rl; r < r_end; r += row_lanes) {
-      const uint4 u = gn_load(src, static_cast<long long>(b) * HW + r, v);
+    auto acc = [&](const uint4 u) {
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -60,6 +81,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
         sum[2 * j + 1] += f.y;
         sq[2 * j + 1] += f.y * f.y;
       }
+    };
+    int r = r_begin + rl;
+    for (; r + 3 * row_lanes < r_end; r += 4 * row_lanes) {   // four independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(src, static_cast<long long>(b) * HW + r + k * row_lanes, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (RESIDENT) gn_rows[(r + k * row_lanes - r_begin) * V + v] = u[k];
+        acc(u[k]);
+      }
+    }
+    for (; r < r_end; r += row_lanes) {
+      const uint4 u = gn_load(src, static_cast<long long>(b) * HW + r, v);
+      if (RESIDENT) gn_rows[(r - r_begin) * V + v] = u;
+      acc(u);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -87,55 +124,60 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(GnSrc src, int HW,
     double* dst = partial + ((static_cast<long long>(b) * gridDim.x + blockIdx.x) * GN_GROUPS + threadIdx.x) * 2;
     dst[0] = a;
     dst[1] = q;
+    __threadfence();   // the partials are visible device-wide before this CTA arrives at the barrier
   }
-}
-
-__global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* partial, const __half* gamma, const __half* beta,
-                float eps, int silu, __half* out) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int C = src.C0 + src.C1;
-  const int V = C / 8;
-  const int cpg = C / GN_GROUPS;
-  const int row_lanes = GN_THREADS / V;
-  const int b = blockIdx.y;
-  const int r_begin = blockIdx.x * rows_per_cta;
-  const int r_end = min(HW, r_begin + rows_per_cta);
-  const int v = threadIdx.x % V;
-  const int rl = threadIdx.x / V;
-  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
-  __shared__ double red_a[GN_THREADS / GN_GROUPS][GN_GROUPS], red_q[GN_THREADS / GN_GROUPS][GN_GROUPS];
+  __syncthreads();
+  // ---------------- per-sample barrier (sense reversal; bounded spin: a bug must trap, not hang the GPU)
+  if (threadIdx.x == 0 && gridDim.x > 1) {
+    const int my = s_sense;
+    if (atomicAdd(&bar[b].count, 1) == static_cast<int>(gridDim.x) - 1) {
+      bar[b].count = 0;
+      __threadfence();
+      atomicExch(&bar[b].sense, my ^ 1);
+    } else {
+      const uint64_t t0 = globaltimer_ns();
+      uint32_t spins = 0;
+      while (*reinterpret_cast<volatile int*>(&bar[b].sense) == my) {
+        __nanosleep(64);
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+          printf("b200vton: groupnorm barrier timeout block(%d,%d)\n", blockIdx.x, blockIdx.y);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---------------- phase 2: total statistics in a fixed order, then apply
   {
-    // stage 2 of the statistics: 16 slices of the chunk list are summed in parallel (fixed order inside a slice, fixed
-    // order across slices), so the serial chain is gridDim.x/16 dependent L2 reads instead of gridDim.x
+    double* red_a = reinterpret_cast<double*>(ps);   // [16][32] doubles = 4 KB each, ps / pq are free now
+    double* red_q = reinterpret_cast<double*>(pq);
     const int g = threadIdx.x & (GN_GROUPS - 1), sl = threadIdx.x / GN_GROUPS;
     double a = 0.0, q = 0.0;
     for (int ch = sl; ch < static_cast<int>(gridDim.x); ch += GN_THREADS / GN_GROUPS) {
-      const double2 pv = *reinterpret_cast<const double2*>(
-          partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + g) * 2);
-      a += pv.x;
-      q += pv.y;
+      const double* pp = partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + g) * 2;
+      a += __ldcg(pp);
+      q += __ldcg(pp + 1);
     }
-    red_a[sl][g] = a;
-    red_q[sl][g] = q;
-  }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    double a = 0.0, q = 0.0;
+    red_a[sl * GN_GROUPS + g] = a;
+    red_q[sl * GN_GROUPS + g] = q;
+    __syncthreads();
+    if (threadIdx.x < GN_GROUPS) {
+      double ta = 0.0, tq = 0.0;
 #pragma unroll
-    for (int sl = 0; sl < GN_THREADS / GN_GROUPS; ++sl) {
-      a += red_a[sl][threadIdx.x];
-      q += red_q[sl][threadIdx.x];
+      for (int s2 = 0; s2 < GN_THREADS / GN_GROUPS; ++s2) {
+        ta += red_a[s2 * GN_GROUPS + threadIdx.x];
+        tq += red_q[s2 * GN_GROUPS + threadIdx.x];
+      }
+      const double n = static_cast<double>(cpg) * HW;
+      const double mean = ta / n;
+      double var = tq / n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      s_mean[threadIdx.x] = static_cast<float>(mean);
+      s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
     }
-    const double n = static_cast<double>(cpg) * HW;
-    const double mean = a / n;
-    double var = q / n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = rsqrtf(static_cast<float>(var) + eps);
+    __syncthreads();
   }
-  __syncthreads();
   if (rl >= row_lanes) return;
   float sc[8], sh[8];
 #pragma unroll
@@ -149,7 +191,7 @@ gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* partial, cons
   }
   for (int r = r_begin + rl; r < r_end; r += row_lanes) {
     const long long row = static_cast<long long>(b) * HW + r;
-    const uint4 u = gn_load(src, row, v);
+    const uint4 u = RESIDENT ? gn_rows[(r - r_begin) * V + v] : gn_load(src, row, v);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     float y[8];
 #pragma unroll
@@ -171,27 +213,67 @@ gn_apply_kernel(GnSrc src, int HW, int rows_per_cta, const double* partial, cons
   }
 }
 
-// stats_ws: max(B, 296) * 64 doubles of scratch (per-(sample, chunk, group) partial sums)
+// stats_ws layout (doubles): [max(B,296) * 64] per-(sample, chunk, group) partial sums, then GN_BAR_BYTES of barrier state
+// (GnBarrier per sample) that must be ZERO before the first launch on this workspace and is left zero-count afterwards.
+constexpr int GN_WS_PARTIAL_DOUBLES = 296 * 64;
+constexpr int GN_MAX_BATCH_BARRIER = 4096;
+
 int groupnorm_impl(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma, const void* beta,
                    float eps, int silu, void* stats_ws, void* out, cudaStream_t stream) {
   const int C = C0 + C1;
   VTON_CHECK_ARG(B > 0 && HW > 0 && C > 0, "groupnorm: empty input");
   VTON_CHECK_ARG(C % GN_GROUPS == 0 && C0 % 8 == 0 && C1 % 8 == 0, "groupnorm: C=%d must divide into 32 groups, sources multiple of 8", C);
   VTON_CHECK_ARG(C / 8 <= GN_THREADS, "groupnorm: C=%d too wide", C);
-  VTON_CHECK_ARG(stats_ws != nullptr, "groupnorm: stats workspace (max(B,296)*64 doubles) required");
+  VTON_CHECK_ARG(stats_ws != nullptr, "groupnorm: stats workspace required (see include/b200vton.h)");
+  VTON_CHECK_ARG(B <= GN_MAX_BATCH_BARRIER, "groupnorm: batch %d > %d", B, GN_MAX_BATCH_BARRIER);
   GnSrc src{static_cast<const __half*>(x0), static_cast<const __half*>(x1), C0, C1};
-  int chunks = 296 / B;
-  if (chunks < 1) chunks = 1;
-  if (chunks > cdiv(HW, 16)) chunks = cdiv(HW, 16);
-  const int rows_per_cta = cdiv(HW, chunks);
-  chunks = cdiv(HW, rows_per_cta);
+  static int max_smem = 0, occ_stream = 0;
+  if (!max_smem) {
+    int dev = 0, optin = 0;
+    VTON_CUDA(cudaGetDevice(&dev));
+    VTON_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes fa;
+    VTON_CUDA(cudaFuncGetAttributes(&fa, gn_fused_kernel<true>));
+    max_smem = optin - static_cast<int>(fa.sharedSizeBytes) - 1024;
+    VTON_CUDA(cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    VTON_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_stream, gn_fused_kernel<false>, GN_THREADS, 0));
+    if (occ_stream < 1) occ_stream = 1;
+    if (occ_stream > 2) occ_stream = 2;
+  }
+  double* partial = static_cast<double*>(stats_ws);
+  const int ws_rows = B > 296 ? B : 296;
+  GnBarrier* bar = reinterpret_cast<GnBarrier*>(partial + static_cast<long long>(ws_rows) * 64);
+  // RESIDENT: one CTA per SM, its rows parked in shared memory
+  int chunks_r = kSMs / B;
+  if (chunks_r > cdiv(HW, 16)) chunks_r = cdiv(HW, 16);
+  bool resident = false;
+  int rows_per_cta = 0, chunks = 0;
+  if (chunks_r >= 1) {
+    rows_per_cta = cdiv(HW, chunks_r);
+    if (static_cast<long long>(rows_per_cta) * C * 2 <= max_smem) {
+      resident = true;
+      chunks = cdiv(HW, rows_per_cta);
+    }
+  }
+  if (!resident) {
+    chunks = (kSMs * occ_stream) / B;   // every CTA of the launch co-resident
+    if (chunks < 1) chunks = 1;         // B > capacity: one CTA per sample, nobody waits for anybody
+    if (chunks > cdiv(HW, 16)) chunks = cdiv(HW, 16);
+    rows_per_cta = cdiv(HW, chunks);
+    chunks = cdiv(HW, rows_per_cta);
+  }
   dim3 grid(chunks, B);
-  VTON_CUDA(launch_kernel(gn_stats_kernel, grid, dim3(GN_THREADS), 0, stream, src, HW, rows_per_cta,
-                          static_cast<double*>(stats_ws)));
-  VTON_CUDA(launch_kernel(gn_apply_kernel, grid, dim3(GN_THREADS), 0, stream, src, HW, rows_per_cta,
-                          static_cast<const double*>(stats_ws), static_cast<const __half*>(gamma),
-                          static_cast<const __half*>(beta), eps, silu, static_cast<__half*>(out)));
-  count_launch(2);
+  if (resident) {
+    VTON_CUDA(launch_kernel(gn_fused_kernel<true>, grid, dim3(GN_THREADS),
+                            static_cast<size_t>(rows_per_cta) * C * 2, stream, src, HW, rows_per_cta, partial, bar,
+                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps, silu,
+                            static_cast<__half*>(out)));
+  } else {
+    VTON_CUDA(launch_kernel(gn_fused_kernel<false>, grid, dim3(GN_THREADS), 0, stream, src, HW, rows_per_cta, partial, bar,
+                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps, silu,
+                            static_cast<__half*>(out)));
+  }
+  count_launch(1);
   return kOk;
 }
 

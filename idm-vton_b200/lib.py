@@ -262,11 +262,16 @@ def cross_attention(q, kt, vt, ki=None, vi=None, heads=None, scale=None, ip_scal
 _gn_ws = {}
 
 
+GN_BARRIER_DOUBLES = 4096      # 8 bytes of barrier state per sample, up to 4096 samples (include/b200vton.h)
+
+
 def _stats_ws(device, B):
+    """GroupNorm workspace: max(B,296)*64 doubles of partial sums followed by the per-sample barrier state, which must be
+    ZERO before first use (the kernel leaves it reusable), hence torch.zeros."""
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _gn_ws.get(key)
-    if ws is None or ws.numel() < max(B, 296) * 64:
-        ws = torch.empty(max(B, 296) * 64, dtype=torch.float64, device=device)
+    if ws is None or ws.numel() < max(B, 296) * 64 + GN_BARRIER_DOUBLES:
+        ws = torch.zeros(max(B, 296) * 64 + GN_BARRIER_DOUBLES, dtype=torch.float64, device=device)
         _gn_ws[key] = ws
     return ws
 

@@ -105,13 +105,17 @@ int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const
 /* fp32 GroupNorm(32 groups)(+SiLU) over dense NHWC [B,HW,C] fp32 — the VAE's norms (diffusers AutoencoderKL
  * ResnetBlock2D.norm1/norm2 + SiLU, Attention.group_norm, conv_norm_out), deterministic two-stage statistics.
  * gamma/beta: [C] fp32 or NULL. stats_ws: scratch of stats_ws_doubles doubles, at least 64 * max(B, 1184) is always
- * enough. EXPERIMENTAL in round 1 (not yet run on hardware; nothing calls it unless B200VTON_VAE_NHWC=1). */
+ * enough. Validated on B200 in round 2; the VAE's default route (B200VTON_VAE_NHWC=0 restores the cuDNN NCHW path). */
 int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps,
                                  int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, void* stream);
 
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
- * fp32 statistics (deterministic two-stage reduction, no atomics), optional SiLU, fp16 out [B*HW, C0+C1].
- * stats_ws: max(B,296)*64 doubles of scratch.
+ * fp32 statistics (deterministic fixed-order reduction, no atomics on data), optional SiLU, fp16 out [B*HW, C0+C1].
+ * ONE launch: statistics, a per-sample barrier between the CTAs of the launch, and the normalisation (the rows stay in
+ * shared memory in between when they fit, so the tensor is read once). B <= 4096.
+ * stats_ws: (max(B,296)*64 + 4096) doubles; the last 4096 doubles hold the barrier state and must be ZERO before the
+ * first call that uses this workspace (the kernel leaves them reusable: no clearing between calls / graph replays).
+ * One workspace must not be shared by launches that may run concurrently (different streams).
  * diffusers ResnetBlock2D.norm1/norm2 (+nonlinearity), Transformer2DModel.norm
  * (src/transformerhacked_tryon.py:329), conv_norm_out + conv_act (src/unet_hacked_tryon.py:1384-1385). */
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,

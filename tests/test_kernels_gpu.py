@@ -220,6 +220,40 @@ def test_groupnorm(lib, B, HW, C0, C1, silu, eps):
     close(out, ref)
 
 
+@pytest.mark.parametrize("B,HW,C0,C1", [(16, 12288, 320, 0),     # hoisted garment chunk: rows do not fit smem (streaming mode)
+                                        (4, 12288, 640, 320),    # up-block skip concat at full resolution (streaming mode)
+                                        (4, 3072, 640, 0),       # resident mode, 37 chunks per sample
+                                        (200, 64, 256, 0),       # more samples than SMs: one CTA per sample, no barrier
+                                        (37, 300, 128, 64)])
+def test_groupnorm_single_launch_modes(lib, B, HW, C0, C1):
+    """The one-launch GroupNorm in both modes (rows parked in shared memory / re-read), across the per-sample barrier:
+    repeated launches on the same workspace (sense reversal) and CUDA-graph replay must be bit-identical."""
+    x0 = rnd(B, HW, C0, seed=1) + 0.5
+    x1 = rnd(B, HW, C1, seed=2) * 2 if C1 else None
+    C = C0 + C1
+    gamma, beta = rnd(C, seed=3), rnd(C, seed=4)
+    n0 = lib.launch_count()
+    out = lib.groupnorm(x0, gamma, beta, 1e-5, True, x1=x1)
+    assert lib.launch_count() - n0 == 1
+    x = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.silu(F.group_norm(x.float().transpose(1, 2), 32, gamma.float(), beta.float(), 1e-5).transpose(1, 2))
+    close(out, ref)
+    for _ in range(3):
+        assert torch.equal(lib.groupnorm(x0, gamma, beta, 1e-5, True, x1=x1), out)
+    st = torch.cuda.Stream()
+    o2 = torch.empty_like(out)
+    with torch.cuda.stream(st):
+        lib.groupnorm(x0, gamma, beta, 1e-5, True, x1=x1, out=o2)      # workspace of this stream allocated outside capture
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            lib.groupnorm(x0, gamma, beta, 1e-5, True, x1=x1, out=o2)
+    o2.zero_()
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o2, out)
+
+
 @pytest.mark.parametrize("rows,C", [(768, 1280), (1000, 640), (33, 2048), (16, 1280)])
 def test_layernorm(lib, rows, C):
     x = rnd(rows, C, seed=1) * 3 + 1
