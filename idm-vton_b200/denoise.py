@@ -60,6 +60,40 @@ def ddpm_step_coefficients(scheduler, t):
     return float(b_t ** 0.5), float(inv_sa), float(c0), float(c1), float(sigma)
 
 
+class GarmentKVCache:
+    """LRU cache of hoisted garment K/V across requests. One entry = the K/V of ONE garment for every
+    denoise step and every try-on block ([T, Ng, 2C] fp16 per block: 4.7 GB at 768x1024 / 30 steps), keyed by the caller's
+    garment id plus everything the values depend on (timestep list, latent size). A hit replaces the garment's T
+    garment-UNet passes (~160 ms per garment on B200) by device-to-device copies (~2 ms)."""
+
+    def __init__(self, max_bytes=40 << 30):
+        import collections
+        self.max_bytes = int(max_bytes)
+        self.entries = collections.OrderedDict()
+        self.bytes = 0
+        self.hits = self.misses = 0
+
+    def get(self, key):
+        e = self.entries.get(key)
+        if e is None:
+            self.misses += 1
+            return None
+        self.entries.move_to_end(key)
+        self.hits += 1
+        return e[0]
+
+    def put(self, key, tensors):
+        n = sum(t.numel() * t.element_size() for t in tensors)
+        if n > self.max_bytes:
+            return
+        if key in self.entries:
+            self.bytes -= self.entries.pop(key)[1]
+        while self.entries and self.bytes + n > self.max_bytes:
+            self.bytes -= self.entries.popitem(last=False)[1][1]
+        self.entries[key] = (tensors, n)
+        self.bytes += n
+
+
 class TryOnDenoiser:
     def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=8, max_kv_bytes=None):
         """max_kv_bytes: budget for the resident garment K/V of the hoisted passes (default: 60% of the free device memory
@@ -136,8 +170,11 @@ class TryOnDenoiser:
         self.ctx_g = self.garment.encode_context(text_embeds_cloth.to(dev, f16), out=self.ctx_g)
         self.aug = self.tryon.aug_embedding(add_text_embeds.to(dev, f16), add_time_ids.to(dev), out=self.aug)
 
-    def set_step_tables(self, scheduler, timesteps):
-        """Uploads the per-step scalars: t and {gs, sqrt(1-abar), 1/sqrt(abar), c0, c1, sigma}."""
+    def set_step_tables(self, scheduler, timesteps, garment_keys=None, cache=None):
+        """Uploads the per-step scalars: t and {gs, sqrt(1-abar), 1/sqrt(abar), c0, c1, sigma}, then runs the hoisted
+        garment passes. garment_keys (one hashable per garment of this batch) + cache (GarmentKVCache): garments whose
+        K/V of all steps are cached are copied in instead of recomputed — valid only when the caller guarantees that a
+        key identifies (cloth latents, text_embeds_cloth); the timestep list and latent size are added to the key here."""
         rows = []
         for t in timesteps:
             rows.append([self.guidance_scale, *ddpm_step_coefficients(scheduler, int(t))])
@@ -157,7 +194,22 @@ class TryOnDenoiser:
                 self.window = max(self.garment_chunk, w // self.garment_chunk * self.garment_chunk) if w >= self.garment_chunk else w
         self.base_table = (torch.arange(T, dtype=torch.int32, device=self.device) % self.window) * self.Bg
         if self.hoist_garment:
+            use_cache = cache is not None and garment_keys is not None and len(garment_keys) == self.Bg and self.window == T
+            if use_cache:
+                sig = (tuple(int(t) for t in timesteps), self.h, self.w)
+                full = [(k, sig) for k in garment_keys]
+                hit = [cache.get(k) for k in full]
+                if all(e is not None for e in hit) and self.gkv_all is not None and self.gkv_all[0].shape[0] == T * self.Bg:
+                    for g, e in enumerate(hit):                         # timestep-major rows: row = t * Bg + g
+                        for dst, src in zip(self.gkv_all, e):
+                            dst.view(T, self.Bg, *dst.shape[1:])[:, g].copy_(src)
+                    self.win_start = 0
+                    return
             self.precompute_garment(0)
+            if use_cache:
+                for g, k in enumerate(full):
+                    if k not in cache.entries:
+                        cache.put(k, [t.view(T, self.Bg, *t.shape[1:])[:, g].clone() for t in self.gkv_all])
 
     def kv_bytes_per_step(self):
         """Bytes of garment K/V one denoise step keeps resident: sum over the try-on blocks of Bg * Ng * 2C fp16."""

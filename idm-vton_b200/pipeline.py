@@ -116,6 +116,7 @@ class StableDiffusionXLInpaintPipeline:
         self._interrupt = False
         self._guidance_scale = 7.5
         self.use_cuda_graph = True
+        self.garment_cache = None      # serving.TryOnServer installs a denoise.GarmentKVCache here (off by default)
 
     # ---------------------------------------------------------------------------------------------
     @classmethod
@@ -520,6 +521,9 @@ class StableDiffusionXLInpaintPipeline:
     ):
         callback = kwargs.pop("callback", None)
         callback_steps = kwargs.pop("callback_steps", None)
+        # extension (serving front-end): one hashable id per garment of this call; with
+        # `self.garment_cache` set, the hoisted garment K/V of known garments are reused instead of recomputed
+        garment_keys = kwargs.pop("garment_keys", None)
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         self.check_inputs(prompt, prompt_2, image, mask_image, height, width, strength, callback_steps, output_type,
@@ -594,7 +598,12 @@ class StableDiffusionXLInpaintPipeline:
         pose_img = self.vae.encode(pose_img.to(self.vae.dtype)).latent_dist.sample().to(prompt_embeds.dtype)
         pose_img = pose_img * self.vae.config.scaling_factor
         pose_img = torch.cat([pose_img] * 2) if self.do_classifier_free_guidance else pose_img
-        cloth = self._encode_vae_image(cloth.to(device=device, dtype=prompt_embeds.dtype), generator=generator)
+        if cloth.shape[1] == self.vae.config.latent_channels:
+            # extension: already-encoded (and scaled) garment latents, as image / masked_image_latents may be (:854-856);
+            # the serving front-end encodes each garment once. No RNG draw happens for the garment in this case.
+            cloth = cloth.to(device=device, dtype=prompt_embeds.dtype)
+        else:
+            cloth = self._encode_vae_image(cloth.to(device=device, dtype=prompt_embeds.dtype), generator=generator)
 
         if trace:
             trace.mark("vae_encode(image, masked, pose, cloth)")
@@ -626,6 +635,12 @@ class StableDiffusionXLInpaintPipeline:
                              "(src/unet_hacked_tryon.py:1234-1242)")
         image_embeds = self.prepare_ip_adapter_image_embeds(ip_adapter_image, device, batch_size * num_images_per_prompt)
         image_embeds = self.unet.encoder_hid_proj(image_embeds).to(prompt_embeds.dtype)      # Resampler, once (:1726)
+        n_img, n_req = image_embeds.shape[0], prompt_embeds.shape[0]
+        if n_img != n_req:          # extension: ONE garment image for all persons of the batch ([uncond ; cond] each x B)
+            if n_req % n_img:
+                raise ValueError(f"ip_adapter_image batch {n_img} does not divide the request batch {n_req}")
+            halves = image_embeds.chunk(2) if self.do_classifier_free_guidance else (image_embeds,)
+            image_embeds = torch.cat([h.repeat_interleave(n_req // n_img, dim=0) for h in halves])
 
         if trace:
             trace.mark("clip_image_encoder+resampler")
@@ -640,7 +655,7 @@ class StableDiffusionXLInpaintPipeline:
         den.prepare(latents, mask, masked_image_latents, pose_img, cloth, prompt_embeds, add_text_embeds, add_time_ids,
                     image_embeds, text_embeds_cloth.to(device), guidance_scale=self.guidance_scale,
                     do_cfg=self.do_classifier_free_guidance)
-        den.set_step_tables(self.scheduler, timesteps)
+        den.set_step_tables(self.scheduler, timesteps, garment_keys=garment_keys, cache=self.garment_cache)
         if trace:
             trace.mark("denoiser.prepare (context K/V, garment passes)")
         with self.progress_bar(total=num_inference_steps) as progress_bar:

@@ -137,6 +137,56 @@ def test_garment_unet_ingests_sdxl_base_checkpoint_keys():
     assert "add_embedding.linear_1.weight" in tnet.state_dict()
 
 
+def test_serving_batches_by_garment_and_encodes_each_garment_once():
+    """serving.TryOnServer on a stand-in pipeline: requests are grouped by garment in arrival order of
+    their oldest member, a batch never mixes garments or exceeds max_batch, every garment is VAE-encoded once and handed
+    to the pipeline as latents + its cache key; tickets map results back to requests."""
+    import types
+    from idm_vton_b200.denoise import GarmentKVCache
+    from idm_vton_b200.serving import TryOnRequest, TryOnServer
+    calls, encodes = [], []
+
+    class FakePipe:
+        _execution_device = torch.device("cpu")
+        unet = types.SimpleNamespace(dtype=torch.float32)
+        garment_cache = None
+
+        def _encode_vae_image(self, image, generator=None):
+            encodes.append(tuple(image.shape))
+            return image[:, :1].repeat(1, 4, 1, 1)[..., ::8, ::8] * 0 + image.mean()
+
+        def __call__(self, **kw):
+            B = kw["prompt_embeds"].shape[0]
+            assert kw["cloth"].shape == (1, 4, 4, 4) and kw["text_embeds_cloth"].shape[0] == 1 and kw["ip_adapter_image"].shape[0] == 1
+            calls.append((B, tuple(kw["garment_keys"]), float(kw["cloth"].mean())))
+            return (kw["image"] + kw["cloth"].mean(),)
+
+    srv = TryOnServer(FakePipe(), height=32, width=32, num_inference_steps=2, max_batch=2, seed=None)
+    assert isinstance(srv.pipe.garment_cache, GarmentKVCache)
+
+    def req(gid, val, with_garment=True):
+        z = torch.zeros
+        return TryOnRequest(garment_id=gid, image=z(3, 32, 32) + val, mask_image=z(1, 32, 32), pose_img=z(3, 32, 32),
+                            prompt_embeds=z(77, 8), negative_prompt_embeds=z(77, 8), pooled_prompt_embeds=z(4),
+                            negative_pooled_prompt_embeds=z(4), cloth=(z(3, 32, 32) + {"A": 1.0, "B": 2.0}[gid]) if with_garment else None,
+                            ip_adapter_image=z(3, 224, 224) if with_garment else None, text_embeds_cloth=z(77, 8) if with_garment else None)
+
+    with pytest.raises(ValueError, match="is new"):
+        srv.submit(req("A", 0.0, with_garment=False))
+    t = [srv.submit(req("A", 0.1)), srv.submit(req("B", 0.2)), srv.submit(req("A", 0.3)), srv.submit(req("A", 0.4, with_garment=False))]
+    out = srv.run()
+    assert calls == [(2, ("A",), 1.0), (1, ("B",), 2.0), (1, ("A",), 1.0)]          # A's oldest first, max_batch 2, then B, then A's rest
+    assert encodes == [(1, 3, 32, 32)] * 2 and srv.stats["garments_encoded"] == 2 and srv.stats["images"] == 4
+    assert sorted(out) == t and abs(float(out[t[3]].mean()) - 1.4) < 1e-6 and abs(float(out[t[1]].mean()) - 2.2) < 1e-6
+    # LRU behaviour of the K/V cache itself
+    c = GarmentKVCache(max_bytes=100)
+    c.put("a", [torch.zeros(10, dtype=torch.float32)])
+    c.put("b", [torch.zeros(10, dtype=torch.float32)])
+    assert c.get("a") is not None
+    c.put("c", [torch.zeros(10, dtype=torch.float32)])                            # evicts b (least recently used)
+    assert c.get("b") is None and c.get("a") is not None and c.get("c") is not None and c.bytes == 80
+
+
 def test_generic_scheduler_interface():
     """the denoiser derives its per-step coefficients from the generic DDPM interface (alphas_cumprod,
     config, num_inference_steps), so the caller's own scheduler object works; unsupported configs raise."""
