@@ -304,3 +304,57 @@ def test_pipeline_rebuilds_denoiser_after_weight_reload(tiny_modules):
     fresh = U.UNet2DConditionModel(cfg_t, R.make_state_dict(cfg_t, seed=77)).to(dev, f16)
     pipe.unet = fresh
     assert torch.equal(run(), b)
+
+
+def test_serving_front_end_garment_batching_and_kv_cache(tiny_modules):
+    """serving.TryOnServer on the engine: persons sharing a garment run as one batch with the garment UNet at batch 1
+    (config 3), a garment seen before skips its garment passes (K/V from the LRU cache) and the result is bit-identical to
+    the uncached run; a batched person equals the same person served alone up to batch-shape effects of the kernels."""
+    from oracle import make_golden_pipeline as MG
+    from idm_vton_b200 import lib as L
+    from idm_vton_b200.pipeline import StableDiffusionXLInpaintPipeline
+    from idm_vton_b200.scheduler import DDPMScheduler
+    from idm_vton_b200.serving import TryOnRequest, TryOnServer
+    dev, f16 = "cuda", torch.float16
+    cfg_t = tiny_modules["cfg_t"]
+
+    def make_pipe():
+        return StableDiffusionXLInpaintPipeline(
+            vae=MG.make_vae().to(dev, f16), text_encoder=None, text_encoder_2=None, tokenizer=None, tokenizer_2=None,
+            unet=tiny_modules["net_t"], unet_encoder=tiny_modules["net_g"], scheduler=DDPMScheduler(),
+            image_encoder=MG.make_image_encoder(cfg_t["resampler"]["embedding_dim"]).to(dev, f16))
+
+    def req(gid, seed):
+        i = MG.make_call_inputs(cfg_t, B=1, seed=seed)
+        gi = MG.make_call_inputs(cfg_t, B=1, seed=1000 + {"A": 1, "B": 2}[gid])      # garment-side tensors depend on the garment only
+        return TryOnRequest(garment_id=gid, image=i["image"][0], mask_image=i["mask_image"][0], pose_img=i["pose_img"][0],
+                            prompt_embeds=i["prompt_embeds"][0], negative_prompt_embeds=i["negative_prompt_embeds"][0],
+                            pooled_prompt_embeds=i["pooled_prompt_embeds"][0],
+                            negative_pooled_prompt_embeds=i["negative_pooled_prompt_embeds"][0], cloth=gi["cloth"][0],
+                            ip_adapter_image=gi["ip_adapter_image"][0], text_embeds_cloth=gi["text_embeds_cloth"][0])
+
+    kw = dict(height=MG.H, width=MG.W, num_inference_steps=3, guidance_scale=2.0, max_batch=4, seed=7)
+    srv = TryOnServer(make_pipe(), **kw)
+    t = [srv.submit(req("A", 1)), srv.submit(req("A", 2)), srv.submit(req("B", 3))]
+    out1 = srv.run()
+    assert srv.stats["batches"] == 2 and srv.stats["garments_encoded"] == 2 and srv.pipe.garment_cache.hits == 0
+    # garment A again: its K/V of all steps come from the cache -> fewer launches, bit-identical images
+    n0 = L.launch_count()
+    t2 = [srv.submit(req("A", 1)), srv.submit(req("A", 2))]
+    out2 = srv.run()
+    cached_launches = L.launch_count() - n0
+    assert srv.pipe.garment_cache.hits == 1 and srv.stats["garments_encoded"] == 2
+    assert torch.equal(out2[t2[0]], out1[t[0]]) and torch.equal(out2[t2[1]], out1[t[1]])
+    srv_nc = TryOnServer(make_pipe(), garment_cache_bytes=0, **kw)
+    n0 = L.launch_count()
+    srv_nc.submit(req("A", 1)), srv_nc.submit(req("A", 2))
+    out3 = srv_nc.run()
+    uncached_launches = L.launch_count() - n0
+    assert torch.equal(out3[0], out1[t[0]]) and cached_launches < uncached_launches
+    # a person served alone vs inside the batch of two: same request, same seeds for the first person of the batch
+    alone = TryOnServer(make_pipe(), garment_cache_bytes=0, **kw)
+    alone.submit(req("A", 1))
+    o_alone = alone.run()[0]
+    d = (o_alone.float() - out1[t[0]].float()).abs()
+    print(f"serving: cached {cached_launches} vs uncached {uncached_launches} eager launches; alone-vs-batched image diff max {d.max():.3e}")
+    assert d.mean().item() < 2e-3
