@@ -34,6 +34,9 @@ int timestep_embed_impl(const void* values, int n, int dim, int rows_repeat, voi
 int skinny_linear_impl(const void* x, int ldx, int M, int K, const void* W, long long ldw, int N, const void* bias,
                        int in_silu, int out_silu, const void* addend, int ld_add, void* out, int ldo,
                        cudaStream_t stream);
+int preprocess_impl(const void* image, const void* mask, int Cm, const void* img_min, int B, int H, int W, int scale,
+                    void* init_image, void* mask_bin, void* masked_image, void* mask_latent, cudaStream_t stream);
+int postprocess_impl(const void* x, int nhwc, int B, int H, int W, void* out_pt, void* out_u8, cudaStream_t stream);
 void set_auto_v2(int on);
 void set_cluster4(int on);
 void set_gemm_deep(int on);
@@ -48,7 +51,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
 
 extern "C" {
 
-int b200vton_version(void) { return 101; }
+int b200vton_version(void) { return 102; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
@@ -159,6 +162,16 @@ int b200vton_skinny_linear(const void* x, int ldx, int M, int K, const void* W, 
 int b200vton_cfg_ddpm_step(const void* eps, int ldc, int B, int C, int H, int W, const void* latents,
                            const void* noise, const void* coef, int do_cfg, void* out, void* stream) {
   return vton::cfg_ddpm_impl(eps, ldc, B, C, H, W, latents, noise, coef, do_cfg, out, S(stream));
+}
+
+int b200vton_preprocess_inpaint(const void* image, const void* mask, int mask_channels, const void* image_min, int B,
+                                int H, int W, int vae_scale, void* init_image, void* mask_bin, void* masked_image,
+                                void* mask_latent, void* stream) {
+  return vton::preprocess_impl(image, mask, mask_channels, image_min, B, H, W, vae_scale, init_image, mask_bin,
+                               masked_image, mask_latent, S(stream));
+}
+int b200vton_postprocess_image(const void* x, int nhwc, int B, int H, int W, void* out_pt, void* out_u8, void* stream) {
+  return vton::postprocess_impl(x, nhwc, B, H, W, out_pt, out_u8, S(stream));
 }
 
 }  // extern "C"

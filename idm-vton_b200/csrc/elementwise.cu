@@ -269,4 +269,88 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
   return kOk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pre / post-processing around the VAE (diffusers VaeImageProcessor as the pipeline uses it,
+// src/tryon_pipeline.py:418-421, 1588-1602, 940-955, 1885). One launch each instead of ~10 small ATen kernels.
+//   preprocess: image [B,3,H,W] fp32 -> init_image = 2x-1 (skipped when the batch already has negative values: diffusers
+//               checks `image.min() < 0`; the minimum arrives as a device scalar, so there is no host sync);
+//               mask [B,Cm,H,W] (Cm = 1 | 3: grayscale 0.299/0.587/0.114) -> binarised at 0.5;
+//               masked_image = init_image * (mask < 0.5);  mask_latent = nearest resize to [B,1,H/s,W/s]
+//               (F.interpolate default: source index = floor(dst * s)).
+//   postprocess: decoder output [B,3,H,W] fp32 (NCHW, or NHWC memory with `nhwc` set) -> (x/2 + 0.5).clamp(0,1) as
+//               fp32 NCHW ("pt") and/or uint8 NHWC (round(x*255): what "np" -> "pil" produces).
+// ------------------------------------------------------------------------------------------------
+__global__ void preprocess_kernel(const float* image, const float* mask_in, int Cm, const float* img_min, int B, int H,
+                                  int W, int s, float* init_image, float* mask_bin, float* masked_image,
+                                  __half* mask_latent) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long HW = static_cast<long long>(H) * W;
+  if (i >= B * HW) return;
+  const int b = static_cast<int>(i / HW);
+  const long long px = i % HW;
+  const bool normalize = !(*img_min < 0.f);
+  float m;
+  if (Cm == 3) {
+    const float* mp = mask_in + static_cast<long long>(b) * 3 * HW + px;
+    // separately rounded products and sums, like the three ATen kernels of the torch expression (no FMA contraction)
+    m = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, mp[0]), __fmul_rn(0.587f, mp[HW])), __fmul_rn(0.114f, mp[2 * HW]));
+  } else {
+    m = mask_in[static_cast<long long>(b) * HW + px];
+  }
+  const float mb = m >= 0.5f ? 1.f : 0.f;
+  mask_bin[i] = mb;
+  const float keep = mb < 0.5f ? 1.f : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long o = (static_cast<long long>(b) * 3 + c) * HW + px;
+    float v = image[o];
+    if (normalize) v = 2.0f * v - 1.0f;
+    init_image[o] = v;
+    masked_image[o] = v * keep;
+  }
+  const int y = static_cast<int>(px / W), x = static_cast<int>(px % W);
+  if (y % s == 0 && x % s == 0 && y / s < H / s && x / s < W / s)
+    mask_latent[(static_cast<long long>(b) * (H / s) + y / s) * (W / s) + x / s] = f2h(mb);
+}
+
+int preprocess_impl(const void* image, const void* mask, int Cm, const void* img_min, int B, int H, int W, int scale,
+                    void* init_image, void* mask_bin, void* masked_image, void* mask_latent, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && H > 0 && W > 0 && (Cm == 1 || Cm == 3) && scale > 0 && H % scale == 0 && W % scale == 0,
+                 "preprocess: bad shape B=%d H=%d W=%d Cm=%d scale=%d", B, H, W, Cm, scale);
+  VTON_CHECK_ARG(image && mask && img_min && init_image && mask_bin && masked_image && mask_latent, "preprocess: null pointer");
+  const long long total = static_cast<long long>(B) * H * W;
+  preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const float*>(image), static_cast<const float*>(mask), Cm, static_cast<const float*>(img_min), B, H, W,
+      scale, static_cast<float*>(init_image), static_cast<float*>(mask_bin), static_cast<float*>(masked_image),
+      static_cast<__half*>(mask_latent));
+  count_launch();
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+__global__ void postprocess_kernel(const float* x, int nhwc, int B, int H, int W, float* out_pt, uint8_t* out_u8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long HW = static_cast<long long>(H) * W;
+  if (i >= B * HW) return;
+  const int b = static_cast<int>(i / HW);
+  const long long px = i % HW;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = nhwc ? x[i * 3 + c] : x[(static_cast<long long>(b) * 3 + c) * HW + px];
+    const float y = fminf(fmaxf(v / 2.f + 0.5f, 0.f), 1.f);
+    if (out_pt) out_pt[(static_cast<long long>(b) * 3 + c) * HW + px] = y;
+    if (out_u8) out_u8[i * 3 + c] = static_cast<uint8_t>(rintf(y * 255.f));
+  }
+}
+
+int postprocess_impl(const void* x, int nhwc, int B, int H, int W, void* out_pt, void* out_u8, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && H > 0 && W > 0 && x && (out_pt || out_u8), "postprocess: bad arguments");
+  const long long total = static_cast<long long>(B) * H * W;
+  postprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const float*>(x), nhwc, B, H, W, static_cast<float*>(out_pt), static_cast<uint8_t*>(out_u8));
+  count_launch();
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 }  // namespace vton

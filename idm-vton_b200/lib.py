@@ -33,10 +33,12 @@ SIGNATURES = {
     "b200vton_timestep_embedding": [_vp, _i, _i, _i, _vp, _vp],
     "b200vton_skinny_linear": [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp],
     "b200vton_cfg_ddpm_step": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
+    "b200vton_preprocess_inpaint": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "b200vton_postprocess_image": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
 }
 
 _lib = None
-ABI_VERSION = 101      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
+ABI_VERSION = 102      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
 
 
 def load(build_if_missing=True):
@@ -384,3 +386,40 @@ def cfg_ddpm_step(eps, latents, noise, coef, do_cfg=True, out=None):
                                     _p(out), _stream())
     _check(rc, "b200vton_cfg_ddpm_step")
     return out
+
+
+def preprocess_inpaint(image, mask, vae_scale=8):
+    """image [B,3,H,W] fp32 CUDA in [0,1] (or already [-1,1]), mask [B,1|3,H,W] fp32 -> (init_image, mask_bin, masked_image,
+    mask_latent fp16 [B,1,H/s,W/s]); one launch, no host sync."""
+    lib = load()
+    B, _, H, W = image.shape
+    assert image.is_cuda and image.dtype == torch.float32 and mask.dtype == torch.float32 and mask.shape[0] == B
+    assert mask.shape[-2:] == image.shape[-2:] and image.is_contiguous() and mask.is_contiguous()
+    img_min = image.amin().reshape(1)
+    init = torch.empty_like(image)
+    masked = torch.empty_like(image)
+    mbin = torch.empty((B, 1, H, W), dtype=torch.float32, device=image.device)
+    mlat = torch.empty((B, 1, H // vae_scale, W // vae_scale), dtype=torch.float16, device=image.device)
+    rc = lib.b200vton_preprocess_inpaint(_p(image), _p(mask), mask.shape[1], _p(img_min), B, H, W, vae_scale, _p(init),
+                                         _p(mbin), _p(masked), _p(mlat), _stream())
+    _check(rc, "b200vton_preprocess_inpaint")
+    return init, mbin, masked, mlat
+
+
+def postprocess_image(x, want_pt=True, want_u8=False):
+    """x: logical [B,3,H,W] fp32 CUDA, contiguous either as NCHW or as channels_last (NHWC memory). Returns
+    (fp32 NCHW in [0,1] or None, uint8 NHWC or None)."""
+    lib = load()
+    B, C, H, W = x.shape
+    assert C == 3 and x.is_cuda and x.dtype == torch.float32
+    nhwc = 0
+    if not x.is_contiguous():
+        if x.is_contiguous(memory_format=torch.channels_last):
+            nhwc = 1
+        else:
+            x = x.contiguous()
+    pt = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device) if want_pt else None
+    u8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
+    rc = lib.b200vton_postprocess_image(_p(x), nhwc, B, H, W, _p(pt), _p(u8), _stream())
+    _check(rc, "b200vton_postprocess_image")
+    return pt, u8

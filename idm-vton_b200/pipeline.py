@@ -355,6 +355,27 @@ class StableDiffusionXLInpaintPipeline:
         if padding_mask_crop is not None:
             raise ValueError("padding_mask_crop is not supported by the B200 engine pipeline (not used by inference.py)")
 
+    def _fused_preprocess_ok(self, image, mask_image, height, width):
+        """The one-launch pre-processing covers what inference.py passes: CUDA float tensors [B,3,H,W] / [B,1|3,H,W]
+        already at the target size (PIL / numpy inputs, resizes and latent-space images take the VaeImageProcessor path)."""
+        ok = lambda t, ch: (torch.is_tensor(t) and t.is_cuda and t.dim() == 4 and t.shape[1] in ch  # noqa: E731
+                            and t.shape[-2] == height and t.shape[-1] == width and torch.is_floating_point(t))
+        return (ok(image, (3,)) and ok(mask_image, (1, 3)) and image.shape[0] == mask_image.shape[0]
+                and height % self.vae_scale_factor == 0 and width % self.vae_scale_factor == 0)
+
+    def _postprocess(self, image, output_type):
+        """VaeImageProcessor.postprocess (src/tryon_pipeline.py:1885); fp32 CUDA decoder outputs take the one-launch kernel
+        (denormalise + clamp, and for "pil" the uint8 NHWC conversion on the device: 4x less D2H)."""
+        if (output_type in ("pt", "pil") and torch.is_tensor(image) and image.is_cuda and image.dtype == torch.float32
+                and image.dim() == 4 and image.shape[1] == 3):
+            from . import lib as L
+            pt, u8 = L.postprocess_image(image, want_pt=output_type == "pt", want_u8=output_type == "pil")
+            if output_type == "pt":
+                return pt
+            import PIL.Image
+            return [PIL.Image.fromarray(a) for a in u8.cpu().numpy()]
+        return self.image_processor.postprocess(image, output_type=output_type)
+
     def _vae32(self):
         """fp32 twin of the VAE for the reference's force_upcast path (src/tryon_pipeline.py:913-915,1076-1093).
         The reference flips the one VAE between fp16 and fp32 around every use; keeping a persistent fp32 copy is the
@@ -416,9 +437,13 @@ class StableDiffusionXLInpaintPipeline:
         return outputs
 
     def prepare_mask_latents(self, mask, masked_image, batch_size, height, width, dtype, device, generator,
-                             do_classifier_free_guidance):
-        """src/tryon_pipeline.py:934-980."""
-        mask = torch.nn.functional.interpolate(mask, size=(height // self.vae_scale_factor, width // self.vae_scale_factor))
+                             do_classifier_free_guidance, _mask_latent=None):
+        """src/tryon_pipeline.py:934-980. `_mask_latent`: the nearest-resized mask when the fused pre-processing kernel
+        already produced it."""
+        if _mask_latent is not None:
+            mask = _mask_latent
+        else:
+            mask = torch.nn.functional.interpolate(mask, size=(height // self.vae_scale_factor, width // self.vae_scale_factor))
         mask = mask.to(device=device, dtype=dtype)
         if mask.shape[0] < batch_size:
             if not batch_size % mask.shape[0] == 0:
@@ -572,14 +597,23 @@ class StableDiffusionXLInpaintPipeline:
         if trace:
             trace.mark("prompt+timesteps")
         # 5. image / mask
-        init_image = self.image_processor.preprocess(image, height=height, width=width).to(dtype=torch.float32)
-        mask = self.mask_processor.preprocess(mask_image, height=height, width=width)
-        if masked_image_latents is not None:
-            masked_image = masked_image_latents
-        elif init_image.shape[1] == 4:
-            masked_image = None
+        mask_latent = None
+        if masked_image_latents is None and self._fused_preprocess_ok(image, mask_image, height, width):
+            # GPU tensors at the target size: image normalisation, mask grayscale + binarisation, the masked image and the
+            # latent-resolution mask in ONE launch (b200vton_preprocess_inpaint; same arithmetic as the two
+            # VaeImageProcessor.preprocess calls below + :1598 + the nearest resize of :940-943)
+            from . import lib as L
+            init_image, mask, masked_image, mask_latent = L.preprocess_inpaint(
+                image.to(torch.float32).contiguous(), mask_image.to(torch.float32).contiguous(), self.vae_scale_factor)
         else:
-            masked_image = init_image * (mask.to(init_image.device) < 0.5)
+            init_image = self.image_processor.preprocess(image, height=height, width=width).to(dtype=torch.float32)
+            mask = self.mask_processor.preprocess(mask_image, height=height, width=width)
+            if masked_image_latents is not None:
+                masked_image = masked_image_latents
+            elif init_image.shape[1] == 4:
+                masked_image = None
+            else:
+                masked_image = init_image * (mask.to(init_image.device) < 0.5)
 
         # 6. latents (RNG draw #1)
         num_channels_latents = self.vae.config.latent_channels
@@ -593,7 +627,7 @@ class StableDiffusionXLInpaintPipeline:
         # 7. mask latents (RNG draw #2), pose latents (global RNG!), cloth latents (RNG draw #3)
         mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, batch_size * num_images_per_prompt,
                                                                height, width, prompt_embeds.dtype, device, generator,
-                                                               self.do_classifier_free_guidance)
+                                                               self.do_classifier_free_guidance, _mask_latent=mask_latent)
         pose_img = pose_img.to(device=device, dtype=prompt_embeds.dtype)
         pose_img = self.vae.encode(pose_img.to(self.vae.dtype)).latent_dist.sample().to(prompt_embeds.dtype)
         pose_img = pose_img * self.vae.config.scaling_factor
@@ -685,7 +719,7 @@ class StableDiffusionXLInpaintPipeline:
             image = vae.decode(latents.to(vae.dtype) / self.vae.config.scaling_factor, return_dict=False)[0]
         # NB (reference quirk, src/tryon_pipeline.py:1868-1885): with output_type == "latent", `image` is still the
         # caller's input image, and that is what gets returned.
-        image = self.image_processor.postprocess(image, output_type=output_type)
+        image = self._postprocess(image, output_type)
         if trace:
             trace.mark("vae_decode+postprocess")
             trace.report()

@@ -155,6 +155,21 @@ int b200vton_skinny_linear(const void* x, int ldx, int M, int K, const void* W, 
 int b200vton_cfg_ddpm_step(const void* eps, int ldc, int B, int C, int H, int W, const void* latents,
                            const void* noise, const void* coef, int do_cfg, void* out, void* stream);
 
+/* Pre-processing of the inpainting inputs in one launch (diffusers VaeImageProcessor.preprocess for image and mask,
+ * the masked image and the latent-resolution mask: src/tryon_pipeline.py:1588-1602, 940-943). image: [B,3,H,W] fp32;
+ * mask: [B,mask_channels,H,W] fp32 (1, or 3 = RGB converted to grayscale); image_min: device scalar = min(image)
+ * (values already in [-1,1], i.e. min < 0, are not normalised again — diffusers' rule, decided on the device);
+ * outputs: init_image, masked_image [B,3,H,W] fp32, mask_bin [B,1,H,W] fp32 (0/1 at threshold 0.5),
+ * mask_latent [B,1,H/vae_scale,W/vae_scale] fp16 (nearest). */
+int b200vton_preprocess_inpaint(const void* image, const void* mask, int mask_channels, const void* image_min, int B,
+                                int H, int W, int vae_scale, void* init_image, void* mask_bin, void* masked_image,
+                                void* mask_latent, void* stream);
+
+/* Post-processing of the VAE decoder output in one launch (VaeImageProcessor.postprocess, src/tryon_pipeline.py:1885):
+ * x [B,3,H,W] fp32 in NCHW memory (nhwc = 0) or NHWC memory (nhwc = 1) -> clamp(x/2 + 0.5, 0, 1) written as fp32 NCHW
+ * (out_pt, may be NULL) and/or uint8 NHWC round(255 y) (out_u8, may be NULL; what "np"/"pil" produce, 4x less D2H). */
+int b200vton_postprocess_image(const void* x, int nhwc, int B, int H, int W, void* out_pt, void* out_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -640,3 +640,31 @@ def test_gemm_deep_pipeline_variant(lib):
         assert torch.equal(g0, lib.gemm(a, wp, bias=bp, geglu=True, force_bn=1256))
     finally:
         lib.set_option("gemm_deep_pipeline", 0)
+
+
+def test_fused_pre_and_postprocessing_match_vae_image_processor(lib):
+    """b200vton_preprocess_inpaint / b200vton_postprocess_image vs the VaeImageProcessor arithmetic the pipeline used before
+    (src/tryon_pipeline.py:1588-1602, 940-943, 1885): bit-exact, including the `min < 0 => already normalised` rule."""
+    from idm_vton_b200.vae import VaeImageProcessor
+    ip = VaeImageProcessor(vae_scale_factor=8)
+    mp = VaeImageProcessor(vae_scale_factor=8, do_normalize=False, do_binarize=True, do_convert_grayscale=True)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W = 2, 64, 48
+    for lo in (0.0, -1.0):                      # [0,1] images are normalised, [-1,1] images are not
+        for cm in (1, 3):
+            image = torch.rand(B, 3, H, W, device="cuda", generator=g) * (1 - lo) + lo
+            mask = torch.rand(B, cm, H, W, device="cuda", generator=g)
+            init, mbin, masked, mlat = lib.preprocess_inpaint(image, mask, 8)
+            r_init = ip.preprocess(image, height=H, width=W).float()
+            r_mask = mp.preprocess(mask, height=H, width=W)
+            assert torch.equal(init, r_init) and torch.equal(mbin, r_mask)
+            assert torch.equal(masked, r_init * (r_mask < 0.5))
+            assert torch.equal(mlat.float(), F.interpolate(r_mask, size=(H // 8, W // 8)))
+    x = torch.randn(B, 3, H, W, device="cuda", generator=g) * 0.8
+    for t in (x, x.contiguous(memory_format=torch.channels_last)):
+        pt, u8 = lib.postprocess_image(t, want_pt=True, want_u8=True)
+        ref = ip.postprocess(x, output_type="pt")
+        assert torch.equal(pt, ref)
+        ref_pil = ip.postprocess(x, output_type="pil")
+        import numpy as np
+        assert all(np.array_equal(np.asarray(p), a) for p, a in zip(ref_pil, u8.cpu().numpy()))
