@@ -10,7 +10,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
 int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                  const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
-                 cudaStream_t stream);
+                 int stride, cudaStream_t stream);
 int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
                      cudaStream_t stream);
 int groupnorm_f32_impl(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps, int silu,
@@ -51,7 +51,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
 
 extern "C" {
 
-int b200vton_version(void) { return 102; }
+int b200vton_version(void) { return 103; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
@@ -97,9 +97,9 @@ int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
 int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int Cin, const void* w, int Cout,
                           const void* bias, const void* temb, int64_t ld_temb, const void* sc0, int C0,
                           const void* sc1, int C1, const void* w_sc, const void* bias_sc, const void* residual,
-                          int64_t ldr, void* out, int64_t ldo, int force_bn, void* stream) {
+                          int64_t ldr, void* out, int64_t ldo, int force_bn, int stride, void* stream) {
   return vton::conv3x3_impl(x, ldx, B, H, W, Cin, w, Cout, bias, temb, ld_temb, sc0, C0, sc1, C1, w_sc, bias_sc,
-                            residual, ldr, out, ldo, force_bn, S(stream));
+                            residual, ldr, out, ldo, force_bn, stride, S(stream));
 }
 
 int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v0, int64_t ldkv0, const void* k1,

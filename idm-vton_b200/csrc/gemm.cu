@@ -100,7 +100,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int tap = s / p.cin_slabs;
             const int c0 = (s - tap * p.cin_slabs) * BK;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 + dx, y0 + dy, b0);
+            tma_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 * p.stride + dx, y0 * p.stride + dy, b0);
             tma_load_2d(b_dst, &tmB, full_bar(stage), c0, tap * p.cout + n0);
           } else {
             tma_load_2d(a_dst, &tmA, full_bar(stage), s * BK, m_tile * BM);
@@ -332,21 +332,30 @@ static void pick_box(int B, int H, int W, int* bw, int* bh, int* bb) {
   (void)B;
 }
 
-static int encode_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W, int C, int ldc, int bw, int bh, int bb) {
+// pixel_step = 2 (stride-2 convolution): the box spans 2*bw x 2*bh input pixels and the TMA traversal stride picks every
+// second one, so the tile that lands in shared memory is the same 128 rows x 64 channels as for stride 1 and the
+// "im2col" of Downsample2D never exists in memory.
+static int encode_nhwc(CUtensorMap* tm, const void* base, int B, int H, int W, int C, int ldc, int bw, int bh, int bb,
+                       int pixel_step = 1) {
   uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                       static_cast<uint64_t>(B)};
   uint64_t strides[3] = {static_cast<uint64_t>(ldc) * 2, static_cast<uint64_t>(W) * ldc * 2,
                          static_cast<uint64_t>(H) * W * ldc * 2};
-  uint32_t box[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
-  return encode_tmap_f16(tm, base, 4, dims, strides, box);
+  uint32_t box[4] = {64, static_cast<uint32_t>(bw * pixel_step), static_cast<uint32_t>(bh * pixel_step),
+                     static_cast<uint32_t>(bb)};
+  uint32_t estr[4] = {1, static_cast<uint32_t>(pixel_step), static_cast<uint32_t>(pixel_step), 1};
+  return encode_tmap_f16(tm, base, 4, dims, strides, box, pixel_step > 1 ? estr : nullptr);
 }
 
-// x: [B,H,W,Cin] (channel stride ldx), w: [9][Cout][Cin] fp16 (tap-major), out: [B*H*W, ldo]
-int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+// x: [B,Hin,Win,Cin] (channel stride ldx), w: [9][Cout][Cin] fp16 (tap-major), out: [B*H*W, ldo] with H = (Hin-1)/stride+1
+int conv3x3_impl(const void* x, long long ldx, int B, int Hin, int Win, int Cin, const void* w, int Cout, const void* bias,
                  const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
-                 cudaStream_t stream) {
-  VTON_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv3x3: empty input");
+                 int stride, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && Hin > 0 && Win > 0, "conv3x3: empty input");
+  VTON_CHECK_ARG(stride == 1 || stride == 2, "conv3x3: stride %d unsupported", stride);
+  VTON_CHECK_ARG(stride == 1 || (!w_sc && !residual), "conv3x3: stride 2 has no shortcut / residual form");
+  const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;   // output size (padding 1)
   VTON_CHECK_ARG(Cin % 64 == 0, "conv3x3: Cin=%d must be a multiple of 64 (pad channels)", Cin);
   VTON_CHECK_ARG(Cout % 8 == 0 && ldo % 8 == 0 && ldx % 8 == 0, "conv3x3: Cout/ldo/ldx must be multiples of 8");
   VTON_CHECK_ARG(C0 % 64 == 0 && C1 % 64 == 0, "conv3x3: shortcut source channels must be multiples of 64");
@@ -358,7 +367,8 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
   VTON_CHECK_ARG(bn2 == 0 || bn2 == 128 || bn2 == 160 || bn2 == 192 || bn2 == 256, "conv3x3: bad 2-CTA tile width %d", bn2);
   const int bn = bn2 ? bn2 : pick_bn(Cout, force_bn >= 1000 ? 0 : force_bn);
   CUtensorMap tmA, tmB, tmS0, tmS1, tmBs;
-  if (int e = encode_nhwc(&tmA, x, B, H, W, Cin, static_cast<int>(ldx), bw, bh, bb)) return e;
+  VTON_CHECK_ARG(stride == 1 || (bw * 2 <= 256 && bh * 2 <= 256), "conv3x3: stride-2 box too large");
+  if (int e = encode_nhwc(&tmA, x, B, Hin, Win, Cin, static_cast<int>(ldx), bw, bh, bb, stride)) return e;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(9) * Cout};
     uint64_t strides[1] = {static_cast<uint64_t>(Cin) * 2};
@@ -395,6 +405,7 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
   p.ld_rowvec = static_cast<int>(ld_temb);
   p.slabs_main = 9 * (Cin / 64);
   p.conv = 1;
+  p.stride = stride;
   p.H = H;
   p.W = W;
   p.B = B;

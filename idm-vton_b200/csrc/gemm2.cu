@@ -138,7 +138,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int tap = s / p.cin_slabs;
             const int c0 = (s - tap * p.cin_slabs) * BK;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma2_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 + dx, y0 + dy, b0);
+            tma2_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 * p.stride + dx, y0 * p.stride + dy, b0);
             tma2_load_2d(b_dst, &tmB, full_bar(stage), c0, tap * p.cout + n0);
           } else {
             if (NP == 2)   // my 64-row half of A slab `rank`, delivered to CTA (0, rank) and CTA (1, rank)

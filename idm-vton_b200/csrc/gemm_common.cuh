@@ -28,6 +28,7 @@ struct GemmParams {
   int cout;       // rows per tap in the packed weight
   int n_tiles;
   int act_gelu;  // v = fp16(gelu_erf(fp16(acc + bias))) before the later epilogue terms (Resampler FeedForward)
+  int stride;    // conv: input pixel step per output pixel (1, or 2 = Downsample2D: the A map steps by 2 pixels per row)
 };
 
 constexpr int BM = 128;

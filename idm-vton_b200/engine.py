@@ -183,7 +183,7 @@ class UNetEngine:
                 if i > 0:
                     lvl["attn"].append(self._pack_t2d(sd, f"down_blocks.{i}.attentions.{j}", ch[i], nh[i], tl[i]))
             if i < n_lvl - 1:
-                lvl["down"] = (pack_conv3x3_s2(self._w(sd, f"down_blocks.{i}.downsamplers.0.conv.weight")),
+                lvl["down"] = (pack_conv3x3(self._w(sd, f"down_blocks.{i}.downsamplers.0.conv.weight")),
                                self._w(sd, f"down_blocks.{i}.downsamplers.0.conv.bias"))
             self.down.append(lvl)
         self.mid_res = [self._pack_resnet(sd, f"mid_block.resnets.{j}", temb_ws, temb_bs) for j in (0, 1)]
@@ -382,9 +382,8 @@ class UNetEngine:
                     x = self._t2d(lvl["attn"][j], x, state)
                 skips.append(x)
             if lvl["down"] is not None:
-                B, Hh, Ww, C = x.shape
-                cols = L.im2col3x3_s2(x)
-                x = L.gemm(cols, lvl["down"][0], bias=lvl["down"][1]).view(B, (Hh - 1) // 2 + 1, (Ww - 1) // 2 + 1, C)
+                # Downsample2D (conv3x3 stride 2 pad 1): the same implicit-GEMM kernel, its A map stepping 2 pixels per row
+                x = L.conv3x3(x, lvl["down"][0], bias=lvl["down"][1], stride=2)
                 skips.append(x)
         x = self._resnet(self.mid_res[0], x, None, temb_all)
         x = self._t2d(self.mid_attn, x, state)

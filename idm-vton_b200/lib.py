@@ -18,7 +18,7 @@ _vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 SIGNATURES = {
     "b200vton_gemm_f16": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
     "b200vton_conv3x3_nhwc": [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i64, _vp, _i, _vp, _i, _vp, _vp, _vp, _i64,
-                              _vp, _i64, _i, _vp],
+                              _vp, _i64, _i, _i, _vp],
     "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i,
                            _vp],
     "b200vton_cross_attention": [_vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _f, _vp],
@@ -38,7 +38,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 102      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
+ABI_VERSION = 103      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
 
 
 def load(build_if_missing=True):
@@ -145,21 +145,21 @@ def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=F
 
 
 def conv3x3(x, w_packed, bias=None, temb=None, sc0=None, sc1=None, w_sc=None, bias_sc=None, residual=None, out=None,
-            force_bn=0):
-    """x: [B,H,W,Cin] NHWC fp16 (contiguous); w_packed: [9,Cout,Cin]; returns [B,H,W,Cout]."""
+            force_bn=0, stride=1):
+    """x: [B,H,W,Cin] NHWC fp16 (contiguous); w_packed: [9,Cout,Cin]; returns [B,Ho,Wo,Cout] (stride 1 or 2, pad 1)."""
     lib = load()
     _f16(x, "x"); _f16(w_packed, "w_packed")
     B, H, W, Cin = x.shape
     assert x.is_contiguous() and w_packed.is_contiguous() and w_packed.shape[0] == 9 and w_packed.shape[2] == Cin
     Cout = w_packed.shape[1]
     if out is None:
-        out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x.device)
+        out = torch.empty((B, (H - 1) // stride + 1, (W - 1) // stride + 1, Cout), dtype=torch.float16, device=x.device)
     C0 = sc0.shape[-1] if sc0 is not None else 0
     C1 = sc1.shape[-1] if sc1 is not None else 0
     rc = lib.b200vton_conv3x3_nhwc(_p(x), Cin, B, H, W, Cin, _p(w_packed), Cout, _p(bias), _p(temb),
                                    temb.stride(0) if temb is not None else 0, _p(sc0), C0, _p(sc1), C1, _p(w_sc),
                                    _p(bias_sc), _p(residual), residual.shape[-1] if residual is not None else 0,
-                                   _p(out), out.shape[-1], force_bn, _stream())
+                                   _p(out), out.shape[-1], force_bn, stride, _stream())
     _check(rc, "b200vton_conv3x3_nhwc")
     return out
 

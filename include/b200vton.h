@@ -56,16 +56,18 @@ int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, vo
                       int K, const void* bias, const void* residual, int64_t ldr, const void* rowvec,
                       int64_t ld_rowvec, int rows_per_sample, int flags, int force_bn, void* stream);
 
-/* NHWC 3x3 convolution, stride 1, pad 1, as implicit GEMM: diffusers ResnetBlock2D.conv1/conv2 (+conv_shortcut),
- * conv_in / conv_out (src/unet_hacked_tryon.py:416,755,1245,1386), the conv of Upsample2D.
- * x: [B,H,W,Cin] with channel stride ldx; w: [9][Cout][Cin] (tap = ky*3+kx); out: [B*H*W, ldo].
+/* NHWC 3x3 convolution, pad 1, stride 1 or 2, as implicit GEMM: diffusers ResnetBlock2D.conv1/conv2 (+conv_shortcut),
+ * conv_in / conv_out (src/unet_hacked_tryon.py:416,755,1245,1386), the conv of Upsample2D, and (stride 2) the conv of
+ * Downsample2D (src/unet_block_hacked_tryon.py:1113,1246): the A operand's tensor map then steps two input pixels per
+ * output pixel (TMA traversal stride), so no im2col buffer exists.
+ * x: [B,H,W,Cin] with channel stride ldx; w: [9][Cout][Cin] (tap = ky*3+kx); out: [B*Ho*Wo, ldo], Ho = (H-1)/stride+1.
  * epi: v = fp16(acc + bias); v = fp16(v + temb[b, n]) (time_emb_proj broadcast add);
  *      1x1 shortcut (w_sc [Cout, C0+C1] over the channel concat of sc0|sc1, accumulated in a second TMEM tile):
  *      s = fp16(acc_sc + bias_sc); v = fp16(s + v);   identity residual: v = fp16(v + residual[m, n]). */
 int b200vton_conv3x3_nhwc(const void* x, int64_t ldx, int B, int H, int W, int Cin, const void* w, int Cout,
                           const void* bias, const void* temb, int64_t ld_temb, const void* sc0, int C0,
                           const void* sc1, int C1, const void* w_sc, const void* bias_sc, const void* residual,
-                          int64_t ldr, void* out, int64_t ldo, int force_bn, void* stream);
+                          int64_t ldr, void* out, int64_t ldo, int force_bn, int stride, void* stream);
 
 /* softmax(Q K^T * scale) V, head_dim 64, keys/values streamed from two segments without concatenation:
  * segment 0 = (k0, v0)[b]; segment 1 = (k1, v1)[base + (b - kv1_off) % mod] for b >= kv1_off, where mod = kv1_mod

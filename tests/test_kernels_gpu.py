@@ -668,3 +668,19 @@ def test_fused_pre_and_postprocessing_match_vae_image_processor(lib):
         ref_pil = ip.postprocess(x, output_type="pil")
         import numpy as np
         assert all(np.array_equal(np.asarray(p), a) for p, a in zip(ref_pil, u8.cpu().numpy()))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(4, 128, 96, 320, 320), (4, 64, 48, 640, 640), (1, 16, 16, 64, 64), (2, 24, 40, 128, 128)])
+def test_conv3x3_stride2_downsample(lib, B, H, W, Cin, Cout):
+    """Downsample2D's conv (3x3, stride 2, pad 1; src/unet_block_hacked_tryon.py:1113,1246) on the implicit-GEMM kernel with
+    a stride-2 TMA traversal — no im2col buffer — vs F.conv2d and vs the round-1 im2col + GEMM formulation."""
+    from idm_vton_b200.engine import pack_conv3x3, pack_conv3x3_s2
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    b = rnd(Cout, seed=3)
+    out = lib.conv3x3(x, pack_conv3x3(w), bias=b, stride=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    close(out, ref)
+    old = lib.gemm(lib.im2col3x3_s2(x), pack_conv3x3_s2(w), bias=b).view_as(out)
+    close(out, old, tol=1e-3)
