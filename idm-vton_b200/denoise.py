@@ -271,6 +271,13 @@ class TryOnDenoiser:
         L.cfg_ddpm_step(self.eps, self.latents, self.noise, self.coef, do_cfg=self.do_cfg, out=self.latents_next)
         self.latents.copy_(self.latents_next)
 
+    # Programmatic dependent launch INSIDE the captured step only (B200VTON_PDL_GRAPH, default below): every kernel node
+    # of the graph is one of this library's kernels, which call griddepcontrol.wait before they allocate tensor memory
+    # or touch global memory, so the set-up of kernel n+1 overlaps the tail of kernel n (+1.3 % of the loop, round 1).
+    # Eager launches — which interleave with cuBLAS / cuDNN / ATen kernels in the pipeline call, where round 1 saw two
+    # stalls before the wait-before-alloc fix — keep plain stream order unless B200VTON_PDL=1 asks otherwise.
+    PDL_IN_GRAPH = __import__("os").environ.get("B200VTON_PDL_GRAPH", "0") == "1"
+
     def capture(self):
         """Capture one step into a CUDA graph (after a warm-up launch on a side stream)."""
         s = torch.cuda.Stream(device=self.device)
@@ -281,8 +288,15 @@ class TryOnDenoiser:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._launch_step()
+        pdl_before = self.L.get_option("programmatic_launch", 0)
+        if self.PDL_IN_GRAPH:
+            self.L.set_option("programmatic_launch", 1)
+        try:
+            with torch.cuda.graph(g):
+                self._launch_step()
+        finally:
+            if self.PDL_IN_GRAPH:
+                self.L.set_option("programmatic_launch", pdl_before)
         self.latents.copy_(keep)
         self._graph = g
 

@@ -80,6 +80,7 @@ def load(build_if_missing=True):
         lib.b200vton_set_option(b"gemm_deep_pipeline", 1)
     if os.environ.get("B200VTON_PDL", "0") == "1":
         lib.b200vton_set_option(b"programmatic_launch", 1)
+        _options["programmatic_launch"] = 1
     if os.environ.get("B200VTON_ATTN2", "1") == "0":
         lib.b200vton_set_option(b"attention_pingpong", 0)
     for name, args in SIGNATURES.items():
@@ -90,8 +91,17 @@ def load(build_if_missing=True):
     return lib
 
 
+_options = {}
+
+
 def set_option(name, value):
     _check(load().b200vton_set_option(name.encode(), int(value)), "b200vton_set_option")
+    _options[name] = int(value)
+
+
+def get_option(name, default=0):
+    """Last value set through set_option / the B200VTON_* environment switches (the C library has no getter)."""
+    return _options.get(name, default)
 
 
 def launch_count():
