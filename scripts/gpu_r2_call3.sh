@@ -5,7 +5,10 @@ mkdir -p gpurun_out
 L=gpurun_out/r2_call3.log
 date > $L
 step() { echo "=== $1" | tee -a $L; shift; ( "$@" ) >> $L 2>&1; echo "    exit $?" | tee -a $L; }
-step "tests changed since call 2" timeout 900 python -m pytest tests -q -m gpu -s --timeout 600 -p no:cacheprovider ${PYTEST_K:+-k "$PYTEST_K"}
+step "memcheck on the test that crashed in call 2" timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_engine_gpu.py -q -m gpu -k "tiny_unets_vs_oracle and 2-16-24" -p no:cacheprovider --timeout 400
+for f in tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_seams_gpu.py tests/test_fullsize_gpu.py; do
+  step "pytest $f (own process)" timeout 900 python -m pytest $f -q -m gpu -s --timeout 600 -p no:cacheprovider
+done
 step "graph-timed small kernels" timeout 300 python - <<'PY'
 import sys, json, torch
 sys.path.insert(0, ".")
