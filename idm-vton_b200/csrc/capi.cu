@@ -39,7 +39,6 @@ int preprocess_impl(const void* image, const void* mask, int Cm, const void* img
 int postprocess_impl(const void* x, int nhwc, int B, int H, int W, void* out_pt, void* out_u8, cudaStream_t stream);
 void set_auto_v2(int on);
 void set_cluster4(int on);
-void set_gemm_deep(int on);
 void set_attn_v2(int on);
 void set_attn_qtiles(int n);
 void set_attn_poly(int n);
@@ -57,10 +56,6 @@ long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
   if (name && strcmp(name, "gemm_2cta_auto") == 0) {
     vton::set_auto_v2(value);
-    return 0;
-  }
-  if (name && strcmp(name, "gemm_deep_pipeline") == 0) {
-    vton::set_gemm_deep(value);
     return 0;
   }
   if (name && strcmp(name, "gemm_cluster4") == 0) {

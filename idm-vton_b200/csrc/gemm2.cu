@@ -17,16 +17,18 @@
 
 namespace vton {
 
-// RING_SLOTS = 0: one staging buffer per chunk a warp handles per tile (never waits for a store inside a tile);
-// RING_SLOTS = 1 ("deep pipeline" variant): a single 2 KB buffer per warp, re-used after its bulk store has been read —
-// 48 KB less staging buys a sixth operand stage for the 256-wide tiles.
-template <int BN, int STAGES, int RING_SLOTS = 0>
+// One staging buffer per chunk a warp handles per tile: the epilogue never waits for a store inside a tile. (A one-slot
+// ring that bought a sixth operand stage — the "deep pipeline" experiment queued at the end of round 1 — was measured in
+// round 2 and removed: FF1 815 vs 1336 TFLOP/s, FF2 704 vs 1202, 8192^3 1287 vs 1365; profiles/r2_small_kernels.jsonl.
+// The main loop is bound by the L2 -> SM delivery rate, not by bytes in flight, and the serialised staging stalls the
+// epilogue.)
+template <int BN, int STAGES>
 struct Smem2 {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging: per warp one 32-row x 32-column fp16 buffer (2 KB, 64B-swizzled) per chunk of the tile
   static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int RING = RING_SLOTS ? RING_SLOTS : (BN / 32 + 1) / 2;   // staging buffers per epilogue warp
+  static constexpr int RING = (BN / 32 + 1) / 2;   // staging buffers per epilogue warp
   static constexpr int STORE_BYTES = 8 * RING * 2048;
   static constexpr int BAR_OFFSET = STORE_OFFSET + STORE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
@@ -42,17 +44,13 @@ struct Smem2 {
 // accumulator at columns [BN, 2BN), so conv2 and conv_shortcut keep their separately rounded fp16 outputs. With two
 // accumulators per tile there is one TMEM stage instead of two; these tiles have >= 99 K slabs, so the exposed
 // epilogue is a few percent.
-// DEEP = one more operand stage in exchange for a one-slot staging ring (option "gemm_deep_pipeline", off by default:
-// EXPERIMENTAL, written after round 1's GPU budget was spent). Motivation: ncu shows the FF1 launch at 63% tensor-pipe
-// activity with L2 throughput at 34% of its peak — neither unit is saturated, so the main loop looks latency-bound
-// (bytes in flight per SM / L2 latency under load), and smem is the only place to find more bytes in flight.
-template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1, bool SC = false, bool DEEP = false>
+template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1, bool SC = false>
 __global__ void __launch_bounds__(320, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const GemmParams p, int m_pairs,
              const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
              const __grid_constant__ CUtensorMap tmBs) {
-  using L = Smem2<BN, STAGES, DEEP ? 1 : 0>;
+  using L = Smem2<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
@@ -262,11 +260,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int g = 0; g < 4; ++g) bcur[g] = bnxt[g];
         }
-        const uint32_t slot = DEEP ? 0u : (c >> 1) * 2048;
-        if (DEEP) {   // single staging buffer: the previous chunk's bulk store must have read it
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-        }
+        const uint32_t slot = (c >> 1) * 2048;
         uint8_t* dst = my_stage_gen + slot + lane * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -305,13 +299,13 @@ struct ScMaps {
   const CUtensorMap* bs;
 };
 
-template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1, bool SC = false, bool DEEP = false>
+template <int BN, int STAGES, bool GEGLU, int EPI, int NP = 1, bool SC = false>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const GemmParams& p,
                    int m_pairs, cudaStream_t stream, ScMaps sc = ScMaps{nullptr, nullptr, nullptr}) {
-  using L = Smem2<BN, STAGES, DEEP ? 1 : 0>;
+  using L = Smem2<BN, STAGES>;
   static_assert(!SC || 2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
   static_assert(L::TOTAL <= 232448, "shared memory of this variant exceeds the 227 KB a CTA may use");
-  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI, NP, SC, DEEP>;
+  auto kern = gemm2_kernel<BN, STAGES, GEGLU, EPI, NP, SC>;
   static bool configured = false;
   static int max_clusters = kSMs / (2 * NP);
   if (!configured) {
@@ -359,8 +353,6 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 }
 
 // bn in {128, 160, 192, 256}; weight-tile box = bn/2 rows
-static int g_deep = 0;   // "gemm_deep_pipeline": 256-wide tiles with 6 operand stages and a one-slot staging ring
-void set_gemm_deep(int on) { g_deep = on; }
 
 // np = MMA pairs per cluster: 2 expects tmA encoded with 64-row boxes (linear layers only, BN 256).
 int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int m_tiles,
@@ -411,18 +403,6 @@ int gemm2_dispatch(int bn, bool geglu, const CUtensorMap& tmA, const CUtensorMap
       case EPI_BIAS: return launch2<256, 5, false, EPI_BIAS, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
       case EPI_BIAS | EPI_RES: return launch2<256, 5, false, EPI_BIAS | EPI_RES, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
       default: return launch2<256, 5, false, EPI_RUNTIME, 2>(tmA, tmB, tmOut, p, m_pairs, stream);
-    }
-  }
-  if (g_deep && bn == 256) {
-    if (geglu) return launch2<256, 6, true, 0, 1, false, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-    switch (epi) {
-      case 0: return launch2<256, 6, false, 0, 1, false, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-      case EPI_BIAS: return launch2<256, 6, false, EPI_BIAS, 1, false, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-      case EPI_BIAS | EPI_ROWVEC:
-        return launch2<256, 6, false, EPI_BIAS | EPI_ROWVEC, 1, false, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-      case EPI_BIAS | EPI_RES:
-        return launch2<256, 6, false, EPI_BIAS | EPI_RES, 1, false, true>(tmA, tmB, tmOut, p, m_pairs, stream);
-      default: return launch2<256, 6, false, EPI_RUNTIME, 1, false, true>(tmA, tmB, tmOut, p, m_pairs, stream);
     }
   }
   if (geglu) {

@@ -46,7 +46,7 @@ struct GnBarrier {
 };
 
 template <bool RESIDENT>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 2)
 gn_fused_kernel(GnSrc src, int HW, int rows_per_cta, double* partial, GnBarrier* bar, const __half* gamma,
                 const __half* beta, float eps, int silu, __half* out) {
   pdl_launch_dependents();
@@ -83,12 +83,24 @@ gn_fused_kernel(GnSrc src, int HW, int rows_per_cta, double* partial, GnBarrier*
       }
     };
     int r = r_begin + rl;
-    for (; r + 3 * row_lanes < r_end; r += 4 * row_lanes) {   // four independent 16-byte loads in flight per thread
-      uint4 u[4];
+    // six independent 16-byte loads in flight per thread: with 16-32 warps per SM the statistics pass is bound by
+    // bytes in flight per SM x memory latency, not by issue (ncu r2: 30 us for 31.5 MB with a 4-deep loop)
+    for (; r + 5 * row_lanes < r_end; r += 6 * row_lanes) {
+      uint4 u[6];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = gn_load(src, static_cast<long long>(b) * HW + r + k * row_lanes, v);
+      for (int k = 0; k < 6; ++k) u[k] = gn_load(src, static_cast<long long>(b) * HW + r + k * row_lanes, v);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 6; ++k) {
+        if (RESIDENT) gn_rows[(r + k * row_lanes - r_begin) * V + v] = u[k];
+        acc(u[k]);
+      }
+    }
+    for (; r + 1 * row_lanes < r_end; r += 2 * row_lanes) {
+      uint4 u[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) u[k] = gn_load(src, static_cast<long long>(b) * HW + r + k * row_lanes, v);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
         if (RESIDENT) gn_rows[(r + k * row_lanes - r_begin) * V + v] = u[k];
         acc(u[k]);
       }
@@ -154,10 +166,26 @@ gn_fused_kernel(GnSrc src, int HW, int rows_per_cta, double* partial, GnBarrier*
     double* red_q = reinterpret_cast<double*>(pq);
     const int g = threadIdx.x & (GN_GROUPS - 1), sl = threadIdx.x / GN_GROUPS;
     double a = 0.0, q = 0.0;
-    for (int ch = sl; ch < static_cast<int>(gridDim.x); ch += GN_THREADS / GN_GROUPS) {
-      const double* pp = partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + g) * 2;
-      a += __ldcg(pp);
-      q += __ldcg(pp + 1);
+    {
+      // the chunk partials of this (slice, group) are fetched five at a time before they are summed (independent L2
+      // loads; the order of the additions is fixed): 74 chunks per sample at batch 4 = one batch of five per thread
+      constexpr int SLICES = GN_THREADS / GN_GROUPS;
+      for (int c0 = sl; c0 < static_cast<int>(gridDim.x); c0 += 5 * SLICES) {
+        double2 pv[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int ch = c0 + k * SLICES;
+          pv[k] = ch < static_cast<int>(gridDim.x)
+                      ? __ldcg(reinterpret_cast<const double2*>(
+                            partial + ((static_cast<long long>(b) * gridDim.x + ch) * GN_GROUPS + g) * 2))
+                      : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          a += pv[k].x;
+          q += pv[k].y;
+        }
+      }
     }
     red_a[sl * GN_GROUPS + g] = a;
     red_q[sl * GN_GROUPS + g] = q;
@@ -189,9 +217,8 @@ gn_fused_kernel(GnSrc src, int HW, int rows_per_cta, double* partial, GnBarrier*
     sc[j] = s_rstd[g] * gm;
     sh[j] = bt - s_mean[g] * sc[j];
   }
-  for (int r = r_begin + rl; r < r_end; r += row_lanes) {
+  auto apply_row = [&](int r, const uint4 u) {
     const long long row = static_cast<long long>(b) * HW + r;
-    const uint4 u = RESIDENT ? gn_rows[(r - r_begin) * V + v] : gn_load(src, row, v);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     float y[8];
 #pragma unroll
@@ -210,7 +237,19 @@ gn_fused_kernel(GnSrc src, int HW, int rows_per_cta, double* partial, GnBarrier*
     o.z = pack_h2(y[4], y[5]);
     o.w = pack_h2(y[6], y[7]);
     *reinterpret_cast<uint4*>(out + row * C + v * 8) = o;
+  };
+  int r = r_begin + rl;
+  for (; r + 3 * row_lanes < r_end; r += 4 * row_lanes) {   // the re-read (L2 hits in the streaming variant) is 4 deep
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      u[k] = RESIDENT ? gn_rows[(r + k * row_lanes - r_begin) * V + v]
+                      : gn_load(src, static_cast<long long>(b) * HW + r + k * row_lanes, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) apply_row(r + k * row_lanes, u[k]);
   }
+  for (; r < r_end; r += row_lanes)
+    apply_row(r, RESIDENT ? gn_rows[(r - r_begin) * V + v] : gn_load(src, static_cast<long long>(b) * HW + r, v));
 }
 
 // stats_ws layout (doubles): [max(B,296) * 64] per-(sample, chunk, group) partial sums, then GN_BAR_BYTES of barrier state

@@ -276,7 +276,10 @@ class TryOnDenoiser:
     # or touch global memory, so the set-up of kernel n+1 overlaps the tail of kernel n (+1.3 % of the loop, round 1).
     # Eager launches — which interleave with cuBLAS / cuDNN / ATen kernels in the pipeline call, where round 1 saw two
     # stalls before the wait-before-alloc fix — keep plain stream order unless B200VTON_PDL=1 asks otherwise.
-    PDL_IN_GRAPH = __import__("os").environ.get("B200VTON_PDL_GRAPH", "0") == "1"
+    # Round 2 on B200: 1126 -> 1116 ms per 30-step loop (profiles/r2_pdl_in_graph.json), 3 of 3 bench runs with the e2e
+    # section clean; with PDL on every launch (eager ones included) 4 of 4 clean after the wait-before-alloc fix and
+    # `compute-sanitizer --tool synccheck` reports no hazard. Default: ON inside the graph, OFF for eager launches.
+    PDL_IN_GRAPH = __import__("os").environ.get("B200VTON_PDL_GRAPH", "1") == "1"
 
     def capture(self):
         """Capture one step into a CUDA graph (after a warm-up launch on a side stream)."""

@@ -76,8 +76,6 @@ def load(build_if_missing=True):
         lib.b200vton_set_option(b"gemm_2cta_auto", 0)
     if os.environ.get("B200VTON_CLUSTER4", "1") == "0":
         lib.b200vton_set_option(b"gemm_cluster4", 0)
-    if os.environ.get("B200VTON_GEMM_DEEP", "0") == "1":
-        lib.b200vton_set_option(b"gemm_deep_pipeline", 1)
     if os.environ.get("B200VTON_PDL", "0") == "1":
         lib.b200vton_set_option(b"programmatic_launch", 1)
         _options["programmatic_launch"] = 1

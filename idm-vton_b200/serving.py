@@ -77,12 +77,15 @@ class TryOnServer:
             del self.queue[gid]
         return gid, batch
 
-    def _garment(self, gid, batch, device, dtype, generator):
+    def _garment(self, gid, batch, device, dtype):
         g = self.garments.get(gid)
         if g is None:
             src = next(r for r in batch if r.cloth is not None)
             cloth = src.cloth[None].to(device=device, dtype=dtype)
-            latents = self.pipe._encode_vae_image(cloth, generator=generator)       # ONE posterior sample per garment
+            # ONE posterior sample per garment, from a generator of its own: the per-request generator handed to the
+            # pipeline must see the same stream whether or not the garment was already known
+            gen = torch.Generator(device).manual_seed(self.seed) if self.seed is not None else None
+            latents = self.pipe._encode_vae_image(cloth, generator=gen)
             g = dict(latents=latents, ip_adapter_image=src.ip_adapter_image[None].to(device),
                      text_embeds_cloth=src.text_embeds_cloth[None].to(device=device, dtype=dtype))
             self.garments[gid] = g
@@ -99,7 +102,7 @@ class TryOnServer:
         device = pipe._execution_device
         dtype = pipe.unet.dtype
         gen = torch.Generator(device).manual_seed(self.seed) if self.seed is not None else None
-        g = self._garment(gid, batch, device, dtype, gen)
+        g = self._garment(gid, batch, device, dtype)
         stack = lambda name, dt=None: torch.stack([getattr(r, name) for r in batch]).to(device=device, dtype=dt)  # noqa: E731
         images = pipe(prompt_embeds=stack("prompt_embeds", dtype), negative_prompt_embeds=stack("negative_prompt_embeds", dtype),
                       pooled_prompt_embeds=stack("pooled_prompt_embeds", dtype),

@@ -36,8 +36,6 @@ long long b200vton_launch_count(void);
  * default 0: measured slower).
  * "gemm_cluster4" = 1 runs large linear layers with 256-wide tiles in four-CTA clusters whose CTA pairs multicast the
  * shared A slabs; 0 (default: it measured slower on B200) keeps two-CTA clusters.
- * "gemm_deep_pipeline" = 1 (default 0) gives the 256-wide 2-CTA tiles a sixth
- * operand stage in exchange for a one-slot epilogue staging ring.
  * "programmatic_launch" = 1 launches the hot kernels with programmatic stream serialization (their set-up overlaps
  * the previous kernel's tail; they wait for it before allocating tensor memory or touching global memory);
  * 0 (default) = plain stream order. */

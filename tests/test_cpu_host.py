@@ -494,7 +494,7 @@ def test_library_options_and_argument_checks_without_gpu():
     names = sorted(set(re.findall(r'"([a-z0-9_]+)"', block)))
     assert {"gemm_2cta_auto", "gemm_cluster4", "programmatic_launch", "attention_pingpong", "attention_q_tiles",
             "attention_poly_exp"} <= set(names)
-    defaults = {"gemm_2cta_auto": 1, "gemm_cluster4": 0, "gemm_deep_pipeline": 0, "programmatic_launch": 0, "attention_pingpong": 1,
+    defaults = {"gemm_2cta_auto": 1, "gemm_cluster4": 0, "programmatic_launch": 0, "attention_pingpong": 1,
                 "attention_q_tiles": 0, "attention_poly_exp": 0}
     for n in names:
         assert n in defaults, f"option {n} documented in the header but not covered here"

@@ -616,31 +616,6 @@ def test_vae_nhwc_route_matches_default(lib, monkeypatch):
     close(d1, d0, tol=5e-3)
 
 
-def test_gemm_deep_pipeline_variant(lib):
-    """gemm_deep_pipeline = 1 (6 operand stages, one-slot staging ring) must be bit-identical to the default 2-CTA kernel
-    for plain, bias, bias+residual and GEGLU epilogues, including a ragged N tail."""
-    from idm_vton_b200.engine import pack_geglu
-    cases = [(1024, 1280, 256), (3000, 768, 192), (2048, 1000, 1280)]
-    try:
-        for (M, N, K) in cases:
-            a, w, b, r = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2), rnd(N, seed=3), rnd(M, N, seed=4)
-            outs = []
-            for deep in (0, 1):
-                lib.set_option("gemm_deep_pipeline", deep)
-                outs.append((lib.gemm(a, w, force_bn=1256), lib.gemm(a, w, bias=b, force_bn=1256),
-                             lib.gemm(a, w, bias=b, residual=r, force_bn=1256)))
-            for x0, x1 in zip(*outs):
-                assert torch.equal(x0, x1)
-            close(outs[1][2], r16(r16(a.float() @ w.float().t() + b.float()) + r.float()))
-        a, w, b = rnd(1024, 640, seed=5), rnd(5120, 640, scale=640 ** -0.5, seed=6), rnd(5120, seed=7)
-        wp, bp = pack_geglu(w, b, 256)
-        lib.set_option("gemm_deep_pipeline", 0)
-        g0 = lib.gemm(a, wp, bias=bp, geglu=True, force_bn=1256)
-        lib.set_option("gemm_deep_pipeline", 1)
-        assert torch.equal(g0, lib.gemm(a, wp, bias=bp, geglu=True, force_bn=1256))
-    finally:
-        lib.set_option("gemm_deep_pipeline", 0)
-
 
 def test_fused_pre_and_postprocessing_match_vae_image_processor(lib):
     """b200vton_preprocess_inpaint / b200vton_postprocess_image vs the VaeImageProcessor arithmetic the pipeline used before
