@@ -143,7 +143,10 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
   const int n0 = n_tile * BN;
   const int out_n0 = GEGLU ? n_tile * (BN / 2) : n0;
   const int out_N = GEGLU ? p.N / 2 : p.N;
-  const __half* rowvec_row = has_rowvec ? p.rowvec + static_cast<long long>(sample) * p.ld_rowvec : nullptr;
+  // Rows outside the output (a conv box whose batch extent exceeds B, the ragged last M tile) carry a sample index past
+  // the [B, ld_rowvec] time-embedding tensor: their values are never stored, so they must not read it either (found by
+  // compute-sanitizer in round 2: a 16-byte read up to bb - B rows past the tensor).
+  const __half* rowvec_row = (has_rowvec && out_row >= 0) ? p.rowvec + static_cast<long long>(sample) * p.ld_rowvec : nullptr;
   const __half* res_row = (has_res && out_row >= 0) ? p.residual + out_row * p.ld_res : nullptr;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -177,7 +180,7 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(round_h(v[j]));
       }
-      if (has_rowvec && col_ok) round_add_h8(v, rowvec_row + ncol);
+      if (has_rowvec && col_ok && rowvec_row != nullptr) round_add_h8(v, rowvec_row + ncol);
       if (RT && p.slabs_sc) {
         float s[8];
 #pragma unroll

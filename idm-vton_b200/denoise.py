@@ -95,7 +95,7 @@ class GarmentKVCache:
 
 
 class TryOnDenoiser:
-    def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=8, max_kv_bytes=None):
+    def __init__(self, tryon: UNetEngine, garment: UNetEngine, hoist_garment=True, garment_chunk=None, max_kv_bytes=None):
         """max_kv_bytes: budget for the resident garment K/V of the hoisted passes (default: 60% of the free device memory
         when the step tables are set). When all denoise steps do not fit (e.g. 1024x1024, 50 steps, batch 4 = 84 GB),
         the steps are hoisted window by window: K/V of `window` consecutive steps are resident at a time and the next
@@ -111,6 +111,8 @@ class TryOnDenoiser:
         self.device = tryon.device
         self._graph = None
         self.hoist_garment = hoist_garment
+        if garment_chunk is None:
+            garment_chunk = int(__import__("os").environ.get("B200VTON_GARMENT_CHUNK", "8"))
         self.garment_chunk = garment_chunk
         self.max_kv_bytes = max_kv_bytes
         self.gkv_all = None
