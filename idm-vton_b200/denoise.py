@@ -112,8 +112,8 @@ class TryOnDenoiser:
         self._graph = None
         self.hoist_garment = hoist_garment
         if garment_chunk is None:
-            garment_chunk = int(__import__("os").environ.get("B200VTON_GARMENT_CHUNK", "8"))
-        self.garment_chunk = garment_chunk
+            garment_chunk = int(__import__("os").environ.get("B200VTON_GARMENT_CHUNK", "0")) or None
+        self._garment_chunk = garment_chunk      # None: as many timesteps per pass as keep the pass at <= 64 samples
         self.max_kv_bytes = max_kv_bytes
         self.gkv_all = None
         self.window = None
@@ -212,6 +212,15 @@ class TryOnDenoiser:
                 for g, k in enumerate(full):
                     if k not in cache.entries:
                         cache.put(k, [t.view(T, self.Bg, *t.shape[1:])[:, g].clone() for t in self.gkv_all])
+
+    @property
+    def garment_chunk(self):
+        """Timesteps batched into one hoisted garment-UNet pass. Measured on B200 at config 2 (2 garments): 8 -> 1096 ms per
+        loop, 15 -> 1085, 30 -> 1081 (fewer, larger launches: 936 instead of 3708 eager launches per loop); default = up to
+        64 samples per pass."""
+        if self._garment_chunk:
+            return self._garment_chunk
+        return max(1, 64 // max(1, getattr(self, "Bg", 1)))
 
     def kv_bytes_per_step(self):
         """Bytes of garment K/V one denoise step keeps resident: sum over the try-on blocks of Bg * Ng * 2C fp16."""

@@ -625,19 +625,43 @@ class StableDiffusionXLInpaintPipeline:
                                               timestep=latent_timestep, is_strength_max=is_strength_max, add_noise=True,
                                               return_noise=True, return_image_latents=False)
         # 7. mask latents (RNG draw #2), pose latents (global RNG!), cloth latents (RNG draw #3)
-        mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, batch_size * num_images_per_prompt,
-                                                               height, width, prompt_embeds.dtype, device, generator,
-                                                               self.do_classifier_free_guidance, _mask_latent=mask_latent)
         pose_img = pose_img.to(device=device, dtype=prompt_embeds.dtype)
-        pose_img = self.vae.encode(pose_img.to(self.vae.dtype)).latent_dist.sample().to(prompt_embeds.dtype)
-        pose_img = pose_img * self.vae.config.scaling_factor
-        pose_img = torch.cat([pose_img] * 2) if self.do_classifier_free_guidance else pose_img
-        if cloth.shape[1] == self.vae.config.latent_channels:
-            # extension: already-encoded (and scaled) garment latents, as image / masked_image_latents may be (:854-856);
-            # the serving front-end encodes each garment once. No RNG draw happens for the garment in this case.
-            cloth = cloth.to(device=device, dtype=prompt_embeds.dtype)
+        cloth_is_latents = cloth.shape[1] == self.vae.config.latent_channels
+        if (masked_image is not None and masked_image.shape[1] == 3 and not cloth_is_latents and not isinstance(generator, list)
+                and self.vae.config.force_upcast and masked_image.shape[1:] == pose_img.shape[1:] == cloth.shape[1:]):
+            # The reference encodes the masked image (:964 via 911-932), the pose image (:1646) and the garment (:1654) in
+            # three VAE passes. The encoder is per-sample (convolutions, per-sample GroupNorm, per-sample attention), so ONE
+            # pass over the concatenated batch gives the same posteriors; the three draws then happen in the reference's
+            # order and from the reference's generators (user generator, GLOBAL generator for the pose, user generator).
+            vae = self._vae32()
+            nb = (masked_image.shape[0], pose_img.shape[0], cloth.shape[0])
+            x = torch.cat([masked_image.to(device=device, dtype=torch.float32), pose_img.float(),
+                           cloth.to(device=device, dtype=torch.float32)])
+            dist = vae.encode(x).latent_dist
+            parts = torch.split(torch.cat([dist.mean, dist.logvar], dim=1), nb)
+            from .vae import DiagonalGaussianDistribution
+            d_m, d_p, d_c = (DiagonalGaussianDistribution(p_) for p_ in parts)
+            sf, dt = self.vae.config.scaling_factor, prompt_embeds.dtype
+            masked_lat = sf * d_m.sample(generator).to(dt)                     # draw #2
+            pose_lat = d_p.sample().to(dt) * sf                                # global RNG, like the reference
+            cloth = sf * d_c.sample(generator).to(dt)                          # draw #3
+            mask, masked_image_latents = self.prepare_mask_latents(mask, masked_lat, batch_size * num_images_per_prompt,
+                                                                   height, width, dt, device, generator,
+                                                                   self.do_classifier_free_guidance, _mask_latent=mask_latent)
+            pose_img = torch.cat([pose_lat] * 2) if self.do_classifier_free_guidance else pose_lat
         else:
-            cloth = self._encode_vae_image(cloth.to(device=device, dtype=prompt_embeds.dtype), generator=generator)
+            mask, masked_image_latents = self.prepare_mask_latents(mask, masked_image, batch_size * num_images_per_prompt,
+                                                                   height, width, prompt_embeds.dtype, device, generator,
+                                                                   self.do_classifier_free_guidance, _mask_latent=mask_latent)
+            pose_img = self.vae.encode(pose_img.to(self.vae.dtype)).latent_dist.sample().to(prompt_embeds.dtype)
+            pose_img = pose_img * self.vae.config.scaling_factor
+            pose_img = torch.cat([pose_img] * 2) if self.do_classifier_free_guidance else pose_img
+            if cloth_is_latents:
+                # extension: already-encoded (and scaled) garment latents, as image / masked_image_latents may be
+                # (:854-856); the serving front-end encodes each garment once. No RNG draw happens for the garment then.
+                cloth = cloth.to(device=device, dtype=prompt_embeds.dtype)
+            else:
+                cloth = self._encode_vae_image(cloth.to(device=device, dtype=prompt_embeds.dtype), generator=generator)
 
         if trace:
             trace.mark("vae_encode(image, masked, pose, cloth)")
