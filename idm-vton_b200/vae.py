@@ -85,6 +85,42 @@ class _Resnet(nn.Module):
         return x + h
 
 
+def _split_tf32(x):
+    """x = hi + lo with hi = x rounded to nearest TF32 (10 mantissa bits) and lo the exact fp32 remainder (|lo| <= 2^-11 |x|)."""
+    hi = ((x.view(torch.int32) + 4096) & -8192).view(torch.float32)   # round half up on the 13 low mantissa bits, then clear them
+    return hi, x - hi
+
+
+def _attention_fp32_3xtf32(q, k, v, chunk=2048):
+    """softmax(q k^T / sqrt(C)) v for the VAE mid block — ONE head of C = 512 channels over H*W tokens (12288 at
+    768x1024), exact fp32 in the reference (SDPA on fp32 tensors with torch's default matmul precision). PyTorch's fp32
+    memory-efficient kernel spends 11.3 ms per batch-2 pass on B200 (no tensor cores). Here every product runs on the TF32
+    tensor cores three times with split operands — a·b ≈ a_hi·b_hi + a_hi·b_lo + a_lo·b_hi, fp32 accumulation — which
+    restores fp32-level accuracy (the dropped a_lo·b_lo term is 2^-22 relative); queries are processed in chunks so the
+    score block stays small. Plain torch.matmul (cuBLAS): host-side plumbing of a SURVEY 8f row, not the hot path."""
+    B, N, C = q.shape
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        kh, kl = _split_tf32(k)
+        vh, vl = _split_tf32(v)
+        kh_t, kl_t = kh.transpose(1, 2), kl.transpose(1, 2)
+        out = torch.empty_like(q)
+        scale = C ** -0.5
+        for c0 in range(0, N, chunk):
+            qh, ql = _split_tf32(q[:, c0:c0 + chunk] * scale)
+            s = torch.baddbmm(torch.baddbmm(torch.bmm(ql, kh_t), qh, kl_t), qh, kh_t)      # small terms first
+            p = torch.softmax(s, dim=-1)
+            ph, pl = _split_tf32(p)
+            out[:, c0:c0 + chunk] = torch.baddbmm(torch.baddbmm(torch.bmm(pl, vh), ph, vl), ph, vh)
+        return out
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+_ATTN_3XTF32 = os.environ.get("B200VTON_VAE_ATTN_3XTF32", "1") == "1"
+
+
 class _Attn(nn.Module):
     """Single-head spatial self-attention of the VAE mid block (diffusers Attention with group_norm, bias=True)."""
 
@@ -101,7 +137,10 @@ class _Attn(nn.Module):
         else:
             t = self.group_norm(x).view(b, c, h * w).transpose(1, 2)
         q, k, v = self.to_q(t), self.to_k(t), self.to_v(t)
-        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+        if _ATTN_3XTF32 and t.is_cuda and t.dtype == torch.float32 and t.shape[1] >= 1024:
+            o = _attention_fp32_3xtf32(q, k, v)
+        else:
+            o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
         o = self.to_out[0](o)
         if _use_nhwc(x):
             return x + o.reshape(b, h, w, c).permute(0, 3, 1, 2)
