@@ -659,3 +659,24 @@ def test_conv3x3_stride2_downsample(lib, B, H, W, Cin, Cout):
     close(out, ref)
     old = lib.gemm(lib.im2col3x3_s2(x), pack_conv3x3_s2(w), bias=b).view_as(out)
     close(out, old, tol=1e-3)
+
+
+def test_vae_attention_3xtf32_matches_fp32_sdpa():
+    """The VAE mid-block attention on split TF32 products (vae._attention_fp32_3xtf32) vs fp64 truth: as accurate as
+    PyTorch's fp32 SDPA (the reference's arithmetic), unlike a single TF32 pass."""
+    from idm_vton_b200.vae import _attention_fp32_3xtf32
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, N, C = 2, 3072, 512
+    q, k, v = (torch.randn(B, N, C, device="cuda", generator=g) * s for s in (1.5, 1.5, 1.0))
+    ref = F.scaled_dot_product_attention(q[:, None].double(), k[:, None].double(), v[:, None].double())[:, 0]
+    o = _attention_fp32_3xtf32(q, k, v, chunk=1024)
+    o32 = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        o_tf32 = torch.softmax((q * C ** -0.5) @ k.transpose(1, 2), -1) @ v
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e, e32, e1 = (x.double() - ref).abs().max().item() for x in (o, o32, o_tf32)
+    print(f"VAE attention vs fp64: 3xTF32 {e:.2e}, fp32 SDPA {e32:.2e}, single TF32 pass {e1:.2e}")
+    assert e <= 4 * e32 + 1e-6 and e < 0.1 * e1
