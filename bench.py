@@ -123,10 +123,10 @@ def load_peaks():
 
 
 # DRAM traffic of one launch of the dominant kernel shape, from `ncu --set full` (dram__bytes_read.sum +
-# dram__bytes_write.sum; see profiles/r1_ncu_final_summary.json). Algorithmic bytes of that launch: A 7.9 MB + W 26.2 MB
-# + out 31.5 MB = 65.5 MB.
-DOMINANT_KERNEL_DRAM_BYTES = 36954112   # 34.14 MB read + 2.81 MB written: the 31.5 MB output stays in the 126 MB L2
-DOMINANT_KERNEL_TRAFFIC_SOURCE = "profiles/r1_ncu_v5_summary.json (ncu --set full, one launch after an L2 flush)"
+# dram__bytes_write.sum; profiles/r2_ncu_summary.json, same numbers as round 1's capture). Algorithmic bytes of that launch:
+# A 7.9 MB + W 26.2 MB + out 31.5 MB = 65.5 MB.
+DOMINANT_KERNEL_DRAM_BYTES = 37605120   # 34.15 MB read + 3.46 MB written: the 31.5 MB output stays in the 126 MB L2
+DOMINANT_KERNEL_TRAFFIC_SOURCE = "profiles/r2_ncu_summary.json (ncu --set full, one launch after an L2 flush; config-2 shape)"
 
 
 def time_dominant_kernel(device, rows, n=20):
