@@ -157,7 +157,7 @@ def time_dominant_kernel(device, rows, n=20):
     avg = sum(ms) / len(ms)
     flops = 2.0 * M * N * K
     return dict(kernel=f"gemm2_kernel<BN=256,STAGES=5,GEGLU> [{M}x{N}x{K}] (FF1 of the C=1280 transformer blocks, "
-                       "2-CTA tcgen05 GEMM family)", ms=avg, n=n, flops=flops, tflops=flops / avg / 1e9)
+                       "2-CTA tcgen05 GEMM family)", ms=avg, n=n, flops=flops, tflops=flops / avg / 1e9, rows=M)
 
 
 class ClockSampler:
@@ -601,7 +601,8 @@ def run_b200(args, rank, world, local):
             # against the measured BURST bf16 peak (kernel timed alone). `step` = the whole timed loop against the
             # SUSTAINED peak (algorithmic FLOPs of SURVEY.md App. B / device time).
             "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
-                         "frac": dom["tflops"] / peaks["tflops_burst"], "traffic": DOMINANT_KERNEL_DRAM_BYTES,
+                         "frac": dom["tflops"] / peaks["tflops_burst"],
+                         "traffic": DOMINANT_KERNEL_DRAM_BYTES if dom.get("rows") == 3072 else None,   # ncu capture = config-2 shape
                          "traffic_source": DOMINANT_KERNEL_TRAFFIC_SOURCE,
                          "kernel": dom["kernel"], "algorithmic_flops_per_launch": dom["flops"],
                          "avg_launch_ms": dom["ms"], "launches_timed": dom["n"], "peak_source": peaks["source"],
