@@ -187,9 +187,12 @@ class TryOnDenoiser:
         if self.hoist_garment:
             budget = self.max_kv_bytes
             if budget is None:
+                # memory this process could still use: free on the device + blocks the caching allocator holds but has
+                # not handed out + the K/V buffers of the previous request, which are overwritten in place
                 free, _ = torch.cuda.mem_get_info(self.device)
+                cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
                 held = sum(g.numel() * 2 for g in self.gkv_all) if self.gkv_all is not None else 0
-                budget = int(0.6 * (free + held))
+                budget = int(0.6 * (free + cached + held))
             per_step = self.kv_bytes_per_step()
             if per_step * T > budget:
                 w = max(1, budget // per_step)
