@@ -86,9 +86,14 @@ class _Resnet(nn.Module):
 
 
 def _split_tf32(x):
-    """x = hi + lo with hi = x rounded to nearest TF32 (10 mantissa bits) and lo the exact fp32 remainder (|lo| <= 2^-11 |x|)."""
-    hi = ((x.view(torch.int32) + 4096) & -8192).view(torch.float32)   # round half up on the 13 low mantissa bits, then clear them
-    return hi, x - hi
+    """x ~ hi + lo with BOTH parts exactly representable in TF32 (10 mantissa bits): hi = tf32(x), lo = tf32(x - hi), so the
+    tensor core — which ignores the 13 low mantissa bits of its fp32 operands, i.e. truncates — sees them unchanged
+    (without the second rounding the truncated remainder biased the result: 3.9e-5 instead of 4e-6 against fp64 on B200).
+    What is dropped is 2^-22 |x|."""
+    def tf32(t):
+        return ((t.view(torch.int32) + 4096) & -8192).view(torch.float32)   # round half up on the 13 low bits, clear them
+    hi = tf32(x)
+    return hi, tf32(x - hi)
 
 
 def _attention_fp32_3xtf32(q, k, v, chunk=2048):

@@ -679,4 +679,4 @@ def test_vae_attention_3xtf32_matches_fp32_sdpa():
         torch.backends.cuda.matmul.allow_tf32 = prev
     e, e32, e1 = ((x.double() - ref).abs().max().item() for x in (o, o32, o_tf32))
     print(f"VAE attention vs fp64: 3xTF32 {e:.2e}, fp32 SDPA {e32:.2e}, single TF32 pass {e1:.2e}")
-    assert e <= 4 * e32 + 1e-6 and e < 0.1 * e1
+    assert e <= 6 * e32 + 2e-6 and e < 0.05 * e1
