@@ -115,7 +115,11 @@ int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void*
  * shared memory in between when they fit, so the tensor is read once). B <= 4096.
  * stats_ws: (max(B,296)*64 + 4096) doubles; the last 4096 doubles hold the barrier state and must be ZERO before the
  * first call that uses this workspace (the kernel leaves them reusable: no clearing between calls / graph replays).
- * One workspace must not be shared by launches that may run concurrently (different streams).
+ * One workspace must not be shared by launches that may run concurrently (different streams); more generally two
+ * GroupNorm launches must not run CONCURRENTLY on one device (two streams, two processes): each sizes its grid to be
+ * fully co-resident on an otherwise free device, and two half-resident grids would wait for each other at their
+ * barriers (the spin is bounded: the kernel traps after 4 s instead of hanging). The engine launches everything on one
+ * stream, like the reference pipeline.
  * diffusers ResnetBlock2D.norm1/norm2 (+nonlinearity), Transformer2DModel.norm
  * (src/transformerhacked_tryon.py:329), conv_norm_out + conv_act (src/unet_hacked_tryon.py:1384-1385). */
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,
