@@ -373,6 +373,12 @@ class UNetEngine:
         cfg = self.cfg
         n_lvl = len(self.ch)
         state = dict(idx=0, ctx=ctx, gfeats=gfeats, n_persons=n_persons, collect=collect, gkv_pre=gkv_pre)
+        div = 2 ** (n_lvl - 1)
+        if x_in.shape[1] % div or x_in.shape[2] % div:
+            # diffusers pads the up path with `upsample_size` when the latent size is not a multiple of the total
+            # downsampling factor (src/unet_hacked_tryon.py:1051-1064); inference.py never gets there (768x1024 -> 128x96)
+            raise NotImplementedError(f"latent size {tuple(x_in.shape[1:3])} must be a multiple of {div} (pixel size a "
+                                      f"multiple of {8 * div}): the reference's `upsample_size` path is not implemented")
         x = L.conv3x3(x_in, self.w_in, bias=self.b_in)
         skips = [x]
         for i, lvl in enumerate(self.down):

@@ -187,6 +187,18 @@ def test_serving_batches_by_garment_and_encodes_each_garment_once():
     assert c.get("b") is None and c.get("a") is not None and c.get("c") is not None and c.bytes == 80
 
 
+def test_engine_rejects_latent_sizes_the_up_path_cannot_match():
+    """Latent sizes that are not a multiple of the total downsampling factor need diffusers' `upsample_size` path
+    (src/unet_hacked_tryon.py:1051-1064), which the engine does not implement: a clear error, not a shape mismatch deep
+    inside the launch sequence."""
+    import types
+    from idm_vton_b200.engine import UNetEngine
+    eng = object.__new__(UNetEngine)
+    eng.L, eng.cfg, eng.ch, eng.kind = types.SimpleNamespace(), {}, (64, 128, 256), "tryon"
+    with pytest.raises(NotImplementedError, match="multiple of 4"):
+        eng._forward(torch.zeros(1, 18, 16, 64), None, None, None, 0, None)
+
+
 def test_generic_scheduler_interface():
     """the denoiser derives its per-step coefficients from the generic DDPM interface (alphas_cumprod,
     config, num_inference_steps), so the caller's own scheduler object works; unsupported configs raise."""
