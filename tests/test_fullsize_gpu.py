@@ -172,3 +172,35 @@ def test_fullsize_hoisted_loop_vs_oracle(full):
     _record(case=f"hoisted loop {run} of {steps} steps B={B} {h}x{w}", latents_absmax=ref.abs().max().item(),
             latents=dict(eng_vs_32=d_eng32, ref16_vs_32=d_ref32, eng_vs_ref16=d_eng16))
     _gate("latents", d_eng32, d_ref32, d_eng16)
+
+
+def test_fullsize_shared_garment_step_vs_oracle(full):
+    """BASELINE config 3 semantics at full size: three persons share ONE garment (garment UNet at batch 1, its K/V indexed
+    by every person through the modulo / base scalars of the attention kernel); one hoisted denoise step vs the oracle loop,
+    which expands the garment features to the batch like the reference would (src/tryon_pipeline.py:1787-1796)."""
+    from oracle import loop_ref as LR
+    from idm_vton_b200.denoise import TryOnDenoiser
+    from idm_vton_b200.scheduler import DDPMScheduler
+    B, h, w, steps = 3, 128, 96, 30
+    inp = LR.synth_loop_inputs(full["cfg_t"], full["cfg_g"], B, h, w, Bg=1, seed=13)
+    inp = {k: (v.half().float() if k != "add_time_ids" else v).cuda() for k, v in inp.items()}
+    noise = torch.randn(B, 4, h, w, generator=torch.Generator().manual_seed(6)).half().float().cuda()
+    den = TryOnDenoiser(full["eng_t"], full["eng_g"])
+    sch = DDPMScheduler()
+    sch.set_timesteps(steps)
+    den.prepare(**inp, guidance_scale=2.0)
+    den.set_step_tables(sch, sch.timesteps)
+    assert den.Bg == 1 and den.gkv_all[0].shape[0] == steps
+    den.step(0, noise.half(), use_graph=True)
+    torch.cuda.synchronize()
+    lat = den.latents.clone()
+    del den
+    with torch.no_grad():
+        ref = LR.denoise_loop(full["sd_t32"], full["cfg_t"], full["sd_g32"], full["cfg_g"], inp, steps, noises=[noise], max_steps=1)
+        with torch.autocast("cuda", dtype=torch.float16):
+            ref16 = LR.denoise_loop(full["sd_t"], full["cfg_t"], full["sd_g"], full["cfg_g"], _cast(inp, torch.float16), steps,
+                                    noises=[noise.half()], max_steps=1)
+    d_eng32, d_ref32, d_eng16 = _err(lat, ref), _err(ref16, ref), _err(lat, ref16)
+    _record(case=f"shared garment, 1 step, B={B} persons / 1 garment {h}x{w}", latents_absmax=ref.abs().max().item(),
+            latents=dict(eng_vs_32=d_eng32, ref16_vs_32=d_ref32, eng_vs_ref16=d_eng16))
+    _gate("latents (shared garment)", d_eng32, d_ref32, d_eng16)
