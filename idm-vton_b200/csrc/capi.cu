@@ -37,6 +37,11 @@ int skinny_linear_impl(const void* x, int ldx, int M, int K, const void* W, long
 int preprocess_impl(const void* image, const void* mask, int Cm, const void* img_min, int B, int H, int W, int scale,
                     void* init_image, void* mask_bin, void* masked_image, void* mask_latent, cudaStream_t stream);
 int postprocess_impl(const void* x, int nhwc, int B, int H, int W, void* out_pt, void* out_u8, cudaStream_t stream);
+int enc_attn_impl(const void* q, long long ldq, const void* k, const void* v, long long ldkv, void* out, long long ldo,
+                  int B, int H, int N, int D, float scale, int causal, cudaStream_t stream);
+int patchify_impl(const void* x, int B, int C, int Hi, int Wi, int P, void* out, int ldk, cudaStream_t stream);
+int token_embed_impl(const void* ids, int rows, int T, int C, int vocab, const void* tok, const void* pos, void* out,
+                     cudaStream_t stream);
 void set_auto_v2(int on);
 void set_cluster4(int on);
 void set_attn_v2(int on);
@@ -50,7 +55,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
 
 extern "C" {
 
-int b200vton_version(void) { return 103; }
+int b200vton_version(void) { return 104; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
@@ -103,6 +108,18 @@ int b200vton_attention(const void* q, int64_t ldq, const void* k0, const void* v
                        void* stream) {
   return vton::attn_impl(q, ldq, k0, v0, ldkv0, k1, v1, ldkv1, out, ldo, B, H, Nq, N0, N1, B1, kv1_off, kv1_mod, kv1_base, scale,
                          accumulate, S(stream));
+}
+
+int b200vton_encoder_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                               int64_t ldo, int B, int H, int N, int D, float scale, int causal, void* stream) {
+  return vton::enc_attn_impl(q, ldq, k, v, ldkv, out, ldo, B, H, N, D, scale, causal, S(stream));
+}
+int b200vton_patchify(const void* x, int B, int C, int Hi, int Wi, int P, void* out, int ldk, void* stream) {
+  return vton::patchify_impl(x, B, C, Hi, Wi, P, out, ldk, S(stream));
+}
+int b200vton_token_embedding(const void* ids, int rows, int T, int C, int vocab, const void* token_embedding,
+                             const void* position_embedding, void* out, void* stream) {
+  return vton::token_embed_impl(ids, rows, T, C, vocab, token_embedding, position_embedding, out, S(stream));
 }
 
 int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const void* vt, int64_t ldkv_t, int Nt,

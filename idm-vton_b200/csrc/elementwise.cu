@@ -353,4 +353,71 @@ int postprocess_impl(const void* x, int nhwc, int B, int H, int W, void* out_pt,
   return kOk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CLIP embedding front ends (transformers CLIPVisionEmbeddings / CLIPTextEmbeddings, called from
+// src/tryon_pipeline.py:468-470 and :592-596).
+// patchify: the stride-P patch convolution of the ViT becomes a GEMM over rows [b, gy, gx] with K = (c, ky, kx) — the
+//           order of the conv weight [Cout, 3, P, P] flattened — zero-padded to a multiple of 64 columns.
+// token_embed: out[r] = fp16(token_embedding[ids[r]] + position_embedding[r % T]).
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const __half* x, int C, int Hi, int Wi, int P, int gh, int gw, int K, int ldk, __half* out,
+                                long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int col = static_cast<int>(i % ldk);
+  const long long row = i / ldk;
+  __half v = __float2half(0.f);
+  if (col < K) {
+    const int kx = col % P, ky = (col / P) % P, c = col / (P * P);
+    const int gx = static_cast<int>(row % gw), gy = static_cast<int>((row / gw) % gh);
+    const long long b = row / (static_cast<long long>(gw) * gh);
+    v = x[((b * C + c) * Hi + gy * P + ky) * Wi + gx * P + kx];
+  }
+  out[i] = v;
+}
+
+int patchify_impl(const void* x, int B, int C, int Hi, int Wi, int P, void* out, int ldk, cudaStream_t stream) {
+  VTON_CHECK_ARG(B > 0 && C > 0 && P > 0 && Hi >= P && Wi >= P, "patchify: bad shape");
+  const int gh = Hi / P, gw = Wi / P, K = C * P * P;
+  VTON_CHECK_ARG(ldk >= K, "patchify: row stride %d < K %d", ldk, K);
+  const long long total = static_cast<long long>(B) * gh * gw * ldk;
+  patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const __half*>(x), C, Hi, Wi, P, gh, gw, K, ldk, static_cast<__half*>(out), total);
+  count_launch();
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+__global__ void token_embed_kernel(const long long* ids, int rows, int T, int V, int vocab, const uint4* tok, const uint4* pos,
+                                   uint4* out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * V) return;
+  const int r = static_cast<int>(i / V), c = static_cast<int>(i % V);
+  long long id = ids[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4 a = tok[id * V + c];
+  const uint4 b = pos[static_cast<long long>(r % T) * V + c];
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = unpack_h2(aw[j]), fb = unpack_h2(bw[j]);
+    o[j] = pack_h2(fa.x + fb.x, fa.y + fb.y);
+  }
+  out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int token_embed_impl(const void* ids, int rows, int T, int C, int vocab, const void* tok, const void* pos, void* out,
+                     cudaStream_t stream) {
+  VTON_CHECK_ARG(rows > 0 && T > 0 && C > 0 && C % 8 == 0 && vocab > 0, "token_embed: bad shape rows=%d T=%d C=%d", rows, T, C);
+  const int V = C / 8;
+  const long long total = static_cast<long long>(rows) * V;
+  token_embed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const long long*>(ids), rows, T, V, vocab, static_cast<const uint4*>(tok), static_cast<const uint4*>(pos),
+      static_cast<uint4*>(out));
+  count_launch();
+  VTON_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 }  // namespace vton

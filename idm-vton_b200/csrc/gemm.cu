@@ -316,7 +316,7 @@ int gemm_f16_impl(const void* A, long long lda, const void* W, long long ldw, vo
   p.ld_rowvec = static_cast<int>(ld_rowvec);
   p.rows_per_sample = rows_per_sample;
   p.slabs_main = K / 64;
-  p.act_gelu = (flags & 2) ? 1 : 0;
+  p.act_gelu = (flags & 4) ? 2 : ((flags & 2) ? 1 : 0);
   if (bn2) return gemm2_dispatch(bn, geglu != 0, tmA, tmB, p, cdiv(M, BM), stream, np);
   return dispatch(bn, geglu != 0, tmA, tmB, tmA, tmA, tmB, p, cdiv(M, BM), stream);
 }

@@ -27,7 +27,8 @@ struct GemmParams {
   int cin_slabs;  // Cin / 64
   int cout;       // rows per tap in the packed weight
   int n_tiles;
-  int act_gelu;  // v = fp16(gelu_erf(fp16(acc + bias))) before the later epilogue terms (Resampler FeedForward)
+  int act_gelu;  // v = fp16(act(fp16(acc + bias))) before the later epilogue terms; 1 = erf-GELU (Resampler FeedForward, CLIP
+                 // ViT-H / bigG MLPs), 2 = quick-GELU (CLIP ViT-L text MLP)
   int stride;    // conv: input pixel step per output pixel (1, or 2 = Downsample2D: the A map steps by 2 pixels per row)
 };
 
@@ -176,9 +177,13 @@ __device__ __forceinline__ void epilogue_math(const GemmParams& p, int n_tile, l
       } else if (has_bias && col_ok) {
         add_h8(v, p.bias + ncol);
       }
-      if (RT && p.act_gelu) {   // rare (Resampler FeedForward): keep it rolled
+      if (RT && p.act_gelu) {   // rare (Resampler FeedForward, CLIP MLPs): keep it rolled
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j) v[j] = gelu_erf_fast(round_h(v[j]));
+        for (int j = 0; j < 8; ++j) {
+          const float x = round_h(v[j]);
+          // 1: erf-GELU; 2: quick-GELU x * sigmoid(1.702 x) (the CLIP ViT-L text encoder's activation)
+          v[j] = p.act_gelu == 2 ? __fdividef(x, 1.0f + __expf(-1.702f * x)) : gelu_erf_fast(x);
+        }
       }
       if (has_rowvec && col_ok && rowvec_row != nullptr) round_add_h8(v, rowvec_row + ncol);
       if (RT && p.slabs_sc) {

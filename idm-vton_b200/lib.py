@@ -22,6 +22,9 @@ SIGNATURES = {
     "b200vton_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i,
                            _vp],
     "b200vton_cross_attention": [_vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _f, _vp],
+    "b200vton_encoder_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _i, _vp],
+    "b200vton_patchify": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "b200vton_token_embedding": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "b200vton_conv3x3_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
     "b200vton_groupnorm_nhwc_f32": [_vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i64, _vp, _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
@@ -38,7 +41,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 103      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
+ABI_VERSION = 104      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
 
 
 def load(build_if_missing=True):
@@ -131,7 +134,8 @@ def _f16(t, name):
 # ------------------------------------------------------------------------------------------------
 # op wrappers
 # ------------------------------------------------------------------------------------------------
-def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=False, gelu=False, out=None, force_bn=0):
+def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=False, gelu=False, out=None, force_bn=0,
+         quick_gelu=False):
     """out[M,N] = epi(a[M,K] @ w[N,K]^T). a / residual / out may be row-strided 2-D views (last dim contiguous)."""
     lib = load()
     _f16(a, "a"); _f16(w, "w")
@@ -146,7 +150,8 @@ def gemm(a, w, bias=None, residual=None, rowvec=None, rows_per_sample=0, geglu=F
         assert residual.shape == (M, n_out) and residual.stride(1) == 1
     rc = lib.b200vton_gemm_f16(_p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
                                _p(residual), residual.stride(0) if residual is not None else 0, _p(rowvec),
-                               rowvec.stride(0) if rowvec is not None else 0, rows_per_sample, int(geglu) | (2 if gelu else 0), force_bn,
+                               rowvec.stride(0) if rowvec is not None else 0, rows_per_sample,
+                               int(geglu) | (2 if gelu else 0) | (4 if quick_gelu else 0), force_bn,
                                _stream())
     _check(rc, "b200vton_gemm_f16")
     return out
@@ -196,6 +201,47 @@ def attention(q, k0, v0, k1=None, v1=None, n1=0, kv1_off=0, heads=None, scale=No
                                 out.stride(1), B, H, Nq, N0, n1, B1, kv1_off, kv1_mod, _p(kv1_base), float(scale),
                                 int(accumulate), _stream())
     _check(rc, "b200vton_attention")
+    return out
+
+
+def encoder_attention(q, k, v, heads, head_dim, scale=None, causal=False, out=None):
+    """CLIP-tower self-attention. q / k / v: [B,N,heads*head_dim] views with contiguous last dim (e.g. the three column
+    blocks of a fused QKV buffer); head_dim 16..96, multiple of 16."""
+    lib = load()
+    _f16(q, "q"); _f16(k, "k"); _f16(v, "v")
+    B, N = q.shape[0], q.shape[1]
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride() == k.stride() and k.shape[:2] == (B, N)
+    assert q.stride(0) == N * q.stride(1) and k.stride(0) == N * k.stride(1)
+    if scale is None:
+        scale = head_dim ** -0.5
+    if out is None:
+        out = torch.empty((B, N, heads * head_dim), dtype=torch.float16, device=q.device)
+    rc = lib.b200vton_encoder_attention(_p(q), q.stride(1), _p(k), _p(v), k.stride(1), _p(out), out.stride(1), B, heads, N,
+                                        head_dim, float(scale), int(causal), _stream())
+    _check(rc, "b200vton_encoder_attention")
+    return out
+
+
+def patchify(x, patch, ldk):
+    """x: [B,C,H,W] fp16 -> [B*(H/P)*(W/P), ldk] rows of (c, ky, kx), zero-padded to ldk columns."""
+    lib = load()
+    _f16(x, "x")
+    B, C, H, W = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B * (H // patch) * (W // patch), ldk), dtype=torch.float16, device=x.device)
+    _check(lib.b200vton_patchify(_p(x), B, C, H, W, patch, _p(out), ldk, _stream()), "b200vton_patchify")
+    return out
+
+
+def token_embedding(ids, tok, pos, T):
+    """ids: int64 [rows] (rows = B*T); out[r] = fp16(tok[ids[r]] + pos[r % T])."""
+    lib = load()
+    _f16(tok, "tok"); _f16(pos, "pos")
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous() and tok.is_contiguous() and pos.is_contiguous()
+    rows, C = ids.numel(), tok.shape[1]
+    out = torch.empty((rows, C), dtype=torch.float16, device=tok.device)
+    _check(lib.b200vton_token_embedding(_p(ids), rows, T, C, tok.shape[0], _p(tok), _p(pos), _p(out), _stream()),
+           "b200vton_token_embedding")
     return out
 
 

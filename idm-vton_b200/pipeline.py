@@ -14,6 +14,7 @@ from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
 import torch
 
+from . import clip as _clip
 from .denoise import TryOnDenoiser
 from .vae import VaeImageProcessor
 
@@ -220,18 +221,23 @@ class StableDiffusionXLInpaintPipeline:
         if not isinstance(image, torch.Tensor):
             image = self.feature_extractor(image, return_tensors="pt").pixel_values
         image = image.to(device=device, dtype=dtype)
+        tower = _clip.tower_for(self.image_encoder)     # the module's weights on the engine's kernels (None: unsupported)
         if output_hidden_states:
-            hs = self.image_encoder(image, output_hidden_states=True).hidden_states[-2]
+            penultimate = (lambda x: tower.vision_hidden(x, -2).to(dtype)) if tower is not None else (
+                lambda x: self.image_encoder(x, output_hidden_states=True).hidden_states[-2])
+            hs = penultimate(image)
             hs = hs.repeat_interleave(num_images_per_prompt, dim=0)
             # the unconditional branch encodes an all-zero image: the same tensor for every call with this encoder,
             # so it is computed once per (shape, dtype, device) and reused
-            key = (tuple(image.shape), image.dtype, str(image.device), id(self.image_encoder), _weights_version(self.image_encoder))
+            key = (tuple(image.shape), image.dtype, str(image.device), id(self.image_encoder), _weights_version(self.image_encoder),
+                   tower is not None)
             if getattr(self, "_uncond_clip_key", None) != key:
-                self._uncond_clip = self.image_encoder(torch.zeros_like(image), output_hidden_states=True).hidden_states[-2]
+                self._uncond_clip = penultimate(torch.zeros_like(image))
                 self._uncond_clip_key = key
             un = self._uncond_clip.repeat_interleave(num_images_per_prompt, dim=0)
             return hs, un
-        emb = self.image_encoder(image).image_embeds.repeat_interleave(num_images_per_prompt, dim=0)
+        emb = (tower.vision_forward(image).image_embeds.to(dtype) if tower is not None
+               else self.image_encoder(image).image_embeds).repeat_interleave(num_images_per_prompt, dim=0)
         return emb, torch.zeros_like(emb)
 
     def prepare_ip_adapter_image_embeds(self, ip_adapter_image, device, num_images_per_prompt):
@@ -257,7 +263,8 @@ class StableDiffusionXLInpaintPipeline:
         lora_scale: Optional[float] = None,
         clip_skip: Optional[int] = None,
     ):
-        """src/tryon_pipeline.py:511-743 (CLIP text encoders are outside the hot path: plain PyTorch)."""
+        """src/tryon_pipeline.py:511-743. fp16 CLIP text encoders on the GPU run on the engine's kernels (clip.ClipTower),
+        anything else through the caller's module as in the reference."""
         device = device or self._execution_device
         prompt = [prompt] if isinstance(prompt, str) else prompt
         batch_size = len(prompt) if prompt is not None else prompt_embeds.shape[0]
@@ -269,8 +276,14 @@ class StableDiffusionXLInpaintPipeline:
             for text, tok, enc in zip(texts, tokenizers, text_encoders):
                 ids = tok(text, padding="max_length", max_length=max_length or tok.model_max_length, truncation=True,
                           return_tensors="pt").input_ids
-                out = enc(ids.to(device), output_hidden_states=True)
-                pooled = out[0]
+                tower = _clip.tower_for(enc)
+                if tower is not None:
+                    out = tower.text_forward(ids.to(device), output_hidden_states=True)
+                    # out[0] of the module: text_embeds with a projection head, else last_hidden_state (:598)
+                    pooled = out.text_embeds if out.text_embeds is not None else out.last_hidden_state
+                else:
+                    out = enc(ids.to(device), output_hidden_states=True)
+                    pooled = out[0]
                 embeds.append(out.hidden_states[-2] if clip_skip is None else out.hidden_states[-(clip_skip + 2)])
             return torch.concat(embeds, dim=-1), pooled
 

@@ -47,7 +47,9 @@ int b200vton_set_option(const char* name, int value);
  * epi: v = fp16(acc + bias[n]); v = fp16(v + rowvec[m / rows_per_sample, n]); v = fp16(v + residual[m, n]).
  * flags & 1 (GEGLU): W/bias rows are tile-interleaved [value | gate] (see engine.pack_geglu) and
  *             out[M, N/2] = fp16(value) * fp16(gelu_erf(fp16(gate))).
- * flags & 2 (GELU): v = fp16(gelu_erf(fp16(acc + bias))) before the rowvec / residual terms (ip_adapter/resampler.py:13-20).
+ * flags & 2 (GELU): v = fp16(gelu_erf(fp16(acc + bias))) before the rowvec / residual terms (ip_adapter/resampler.py:13-20;
+ *             the CLIP ViT-H / bigG MLPs). flags & 4 (quick-GELU): v = fp16(x * sigmoid(1.702 x)), x = fp16(acc + bias)
+ *             (the CLIP ViT-L text encoder's MLP, src/tryon_pipeline.py:592).
  * K % 64 == 0; N, lda, ldw, ldo % 8 == 0. force_bn: 0 = automatic kernel and tile width; 64/128/160/256 = 1-CTA
  * kernel with that tile width; 1000 + {128,160,192,256} = 2-CTA persistent kernel (cta_group::2) with that width. */
 int b200vton_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M, int N,
@@ -152,6 +154,25 @@ int b200vton_timestep_embedding(const void* values, int n, int dim, int rows_rep
 int b200vton_skinny_linear(const void* x, int ldx, int M, int K, const void* W, int64_t ldw, int N, const void* bias,
                            int in_silu, int out_silu, const void* addend, int ld_add, void* out, int ldo,
                            void* stream);
+
+/* Encoder self-attention for the CLIP towers around the loop: replaces transformers' CLIPAttention
+ * inside `self.image_encoder(image, output_hidden_states=True)` (src/tryon_pipeline.py:468-470: ViT-H, 16 heads of 80,
+ * 257 tokens, no mask) and inside `text_encoder(text_input_ids, output_hidden_states=True)` (src/tryon_pipeline.py:592-596:
+ * heads of 64, 77 tokens, causal mask). q / k / v: [B, N, >= H*D] views with row strides ldq / ldkv (the three column
+ * blocks of a fused QKV projection buffer); out: [B, N, H*D], row stride ldo. D = 16..96, multiple of 16.
+ * out = softmax(scale * q k^T [+ causal mask]) v per head, fp32 softmax, fp16 probabilities, fp32 accumulation. */
+int b200vton_encoder_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                               int64_t ldo, int B, int H, int N, int D, float scale, int causal, void* stream);
+
+/* CLIPVisionEmbeddings.patch_embedding as a GEMM operand (src/tryon_pipeline.py:468): x [B,C,Hi,Wi] fp16 ->
+ * out [B*(Hi/P)*(Wi/P), ldk] fp16, row = (b, gy, gx), column = (c, ky, kx) = the flattened conv weight's K order;
+ * columns >= C*P*P are written as zeros (ldk = K rounded up to a multiple of 64 for b200vton_gemm_f16). */
+int b200vton_patchify(const void* x, int B, int C, int Hi, int Wi, int P, void* out, int ldk, void* stream);
+
+/* CLIPTextEmbeddings (src/tryon_pipeline.py:592): out[r, :] = fp16(token_embedding[ids[r], :] + position_embedding[r % T, :]);
+ * ids: int64 [rows] on the device (clamped to [0, vocab)); C % 8 == 0. */
+int b200vton_token_embedding(const void* ids, int rows, int T, int C, int vocab, const void* token_embedding,
+                             const void* position_embedding, void* out, void* stream);
 
 /* CFG combine + DDPMScheduler.step (src/tryon_pipeline.py:1814-1823). eps NHWC [2B,HW,ldc] (uncond first) or [B,..]
  * when do_cfg == 0; latents/noise/out NCHW [B,C,H,W] (noise may be NULL); coef: 6 fp32 on device

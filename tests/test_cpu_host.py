@@ -290,6 +290,37 @@ def test_c_abi_exports_every_declared_symbol():
     assert rc == 1 and b"out of range" in l.b200vton_last_error()
 
 
+def test_clip_tower_packing_and_dispatch_on_cpu():
+    """clip.ClipTower packs a transformers CLIP module's own state dict (fused QKV, zero-padded patch weight, class token +
+    position 0); tower_for() leaves CPU / fp32 modules to the caller; the encoder-attention entry point validates its
+    arguments before any CUDA work."""
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection, CLIPVisionConfig, CLIPVisionModelWithProjection
+    from idm_vton_b200 import lib
+    from idm_vton_b200.clip import ClipTower, tower_for
+    cfg = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=28,
+                           patch_size=14, projection_dim=64, hidden_act="gelu")
+    m = CLIPVisionModelWithProjection(cfg).eval()
+    assert tower_for(m) is None                                   # CPU module: the caller's own path
+    t = ClipTower(m.state_dict(), cfg, "vision", "cpu")
+    sd = m.state_dict()
+    assert t.D == 64 and t.K == 588 and t.Kp == 640 and t.w_patch.shape == (128, 640) and not t.w_patch[:, 588:].any()
+    assert torch.equal(t.w_patch[:, :588], sd["vision_model.embeddings.patch_embedding.weight"].half().reshape(128, 588))
+    assert torch.equal(t.blocks[1].wqkv[128:256], sd["vision_model.encoder.layers.1.self_attn.k_proj.weight"].half())
+    assert torch.equal(t.blocks[0].bqkv[256:], sd["vision_model.encoder.layers.0.self_attn.v_proj.bias"].half())
+    pos = sd["vision_model.embeddings.position_embedding.weight"].half()
+    assert torch.equal(t.cls_pos0, sd["vision_model.embeddings.class_embedding"].half() + pos[0]) and t.pos_patches.shape == (4, 128)
+    tc = CLIPTextConfig(vocab_size=100, hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=1,
+                        max_position_embeddings=77, projection_dim=32, hidden_act="quick_gelu", eos_token_id=99)
+    tt = ClipTower(CLIPTextModelWithProjection(tc).state_dict(), tc, "text", "cpu")
+    assert tt.act == {"quick_gelu": True} and tt.proj.shape == (32, 64) and tt.eos_token_id == 99
+    with pytest.raises(ValueError):
+        ClipTower(m.state_dict(), dict(hidden_size=96, num_attention_heads=4, num_hidden_layers=2, intermediate_size=192,
+                                       hidden_act="gelu"), "vision", "cpu")
+    l = lib.load()
+    rc = l.b200vton_encoder_attention(None, 8, None, None, 8, None, 8, 1, 1, 16, 72, 1.0, 0, None)
+    assert rc == 1 and b"head dim" in l.b200vton_last_error()
+
+
 def test_product_does_not_import_oracle():
     """The product path must never route through the oracle or any CPU fallback."""
     pkg = os.path.join(ROOT, "idm-vton_b200")
