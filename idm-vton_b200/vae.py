@@ -1,12 +1,13 @@
-"""AutoencoderKL (SDXL VAE) and VaeImageProcessor stand-ins in plain PyTorch — HOST-SIDE PLUMBING, not the hot path.
+"""AutoencoderKL (SDXL VAE) and VaeImageProcessor stand-ins — HOST-SIDE PLUMBING around the hot path.
 
 The reference pipeline receives a diffusers `AutoencoderKL` as a component (src/tryon_pipeline.py:387-401) and calls
 `vae.encode(x).latent_dist.sample(generator)`, `vae.decode(z, return_dict=False)[0]`, `vae.config.{scaling_factor,
 force_upcast,latent_channels,block_out_channels}` (:911-932,1646,1868-1880). diffusers is not installable in this image, so
 this module supplies an architecture-compatible VAE (same parameter names as diffusers 0.25.0's AutoencoderKL, restated
-from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): its 3x3
-convolutions have an engine kernel (`_conv` -> `b200vton_conv3x3_nhwc_f32`, TF32 tensor cores, opt-in: see the note at
-`_ENGINE_CONV`); norms, the mid-block attention, resampling and the tiny-channel convolutions are PyTorch.
+from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): on a GPU
+the fp32 VAE runs NHWC with its 3x3 / stride-1 convolutions on `b200vton_conv3x3_nhwc_f32` (TF32 tcgen05) and every
+GroupNorm(+SiLU) on `b200vton_groupnorm_nhwc_f32` (default ON, see `_ENGINE_NHWC`); the mid-block attention is a split-TF32
+formulation on cuBLAS; resampling, the stride-2 / 3-8-channel / 1x1 convolutions and the residual adds are PyTorch.
 """
 import os
 import types
