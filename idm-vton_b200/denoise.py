@@ -204,7 +204,13 @@ class TryOnDenoiser:
                 sig = (tuple(int(t) for t in timesteps), self.h, self.w)
                 full = [(k, sig) for k in garment_keys]
                 hit = [cache.get(k) for k in full]
-                if all(e is not None for e in hit) and self.gkv_all is not None and self.gkv_all[0].shape[0] == T * self.Bg:
+                if all(e is not None for e in hit):
+                    if self.gkv_all is None or self.gkv_all[0].shape[0] != T * self.Bg:
+                        # first request of this shape (prepare() dropped the static buffers): allocate them from the cached
+                        # entries' geometry instead of re-running the garment passes; the step graph is captured afterwards
+                        self.gkv_all = [torch.empty((T * self.Bg, *src.shape[1:]), dtype=src.dtype, device=self.device)
+                                        for src in hit[0]]
+                        self._graph = None
                     for g, e in enumerate(hit):                         # timestep-major rows: row = t * Bg + g
                         for dst, src in zip(self.gkv_all, e):
                             dst.view(T, self.Bg, *dst.shape[1:])[:, g].copy_(src)

@@ -104,14 +104,22 @@ class TryOnServer:
         gen = torch.Generator(device).manual_seed(self.seed) if self.seed is not None else None
         g = self._garment(gid, batch, device, dtype)
         stack = lambda name, dt=None: torch.stack([getattr(r, name) for r in batch]).to(device=device, dtype=dt)  # noqa: E731
-        images = pipe(prompt_embeds=stack("prompt_embeds", dtype), negative_prompt_embeds=stack("negative_prompt_embeds", dtype),
-                      pooled_prompt_embeds=stack("pooled_prompt_embeds", dtype),
-                      negative_pooled_prompt_embeds=stack("negative_pooled_prompt_embeds", dtype),
-                      num_inference_steps=self.num_inference_steps, generator=gen, strength=1.0,
-                      pose_img=stack("pose_img", dtype), text_embeds_cloth=g["text_embeds_cloth"], cloth=g["latents"],
-                      mask_image=stack("mask_image"), image=stack("image"), height=self.height, width=self.width,
-                      ip_adapter_image=g["ip_adapter_image"], guidance_scale=self.guidance_scale,
-                      output_type=self.output_type, garment_keys=[gid])[0]
+        # The reference draws the pose latents' posterior sample from the GLOBAL generator (src/tryon_pipeline.py:1646 passes no
+        # generator), so a seeded server would still not be reproducible: with a seed, the global CPU / device generators are
+        # forked around the call and seeded too (their state outside the call is untouched).
+        import contextlib
+        dev_idx = [torch.device(device).index or 0] if torch.device(device).type == "cuda" else []
+        with (torch.random.fork_rng(devices=dev_idx) if self.seed is not None else contextlib.nullcontext()):
+            if self.seed is not None:
+                torch.manual_seed(self.seed)
+            images = pipe(prompt_embeds=stack("prompt_embeds", dtype), negative_prompt_embeds=stack("negative_prompt_embeds", dtype),
+                          pooled_prompt_embeds=stack("pooled_prompt_embeds", dtype),
+                          negative_pooled_prompt_embeds=stack("negative_pooled_prompt_embeds", dtype),
+                          num_inference_steps=self.num_inference_steps, generator=gen, strength=1.0,
+                          pose_img=stack("pose_img", dtype), text_embeds_cloth=g["text_embeds_cloth"], cloth=g["latents"],
+                          mask_image=stack("mask_image"), image=stack("image"), height=self.height, width=self.width,
+                          ip_adapter_image=g["ip_adapter_image"], guidance_scale=self.guidance_scale,
+                          output_type=self.output_type, garment_keys=[gid])[0]
         self.stats["batches"] += 1
         self.stats["images"] += len(batch)
         return {r.ticket: images[i] for i, r in enumerate(batch)}
