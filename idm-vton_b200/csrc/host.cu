@@ -18,10 +18,10 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return g_err; }
 
-// Off by default: it gained 1.3% of the loop on B200, but two bench runs that mix these kernels with cuBLAS/cuDNN
-// kernels (the end-to-end pipeline call) hung while every engine-only run was clean; the suspected cause — a dependent
-// CTA holding tensor memory while it waits for a primary that has not allocated yet — is removed (the kernels now wait
-// BEFORE tcgen05.alloc), but that fix has not been re-validated on hardware yet.
+// Off by default for eager launches, switched on by denoise.py for the kernel nodes of the captured step graph. Round 1 saw
+// two stalls with it on every launch: a dependent CTA held all tensor memory while it waited for a primary that had not
+// allocated yet. The kernels now wait BEFORE tcgen05.alloc; re-validated on B200 in round 2 (4 of 4 bench runs with PDL on
+// every launch clean, compute-sanitizer synccheck / memcheck clean: profiles/r2_compute_sanitizer.md, r2_pdl_in_graph.json).
 static std::atomic<int> g_pdl{0};
 int pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
 void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
