@@ -321,6 +321,88 @@ def test_clip_tower_packing_and_dispatch_on_cpu():
     assert rc == 1 and b"head dim" in l.b200vton_last_error()
 
 
+def test_clip_tower_control_flow_on_cpu(monkeypatch):
+    """The towers' launch sequence (which hidden state index -2 is, class token / position wiring, causal text attention,
+    EOS pooling, projection heads) checked on CPU: the lib wrappers are replaced by plain-torch stand-ins of the kernels'
+    contracts (fp16 in, fp32 arithmetic, fp16 out) and the results compared with the transformers modules in fp32.
+    (The kernels themselves: tests/test_clip_gpu.py.)"""
+    import torch.nn.functional as F
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection, CLIPVisionConfig, CLIPVisionModelWithProjection
+    from idm_vton_b200 import clip as CL
+
+    def gemm(a, w, bias=None, residual=None, gelu=False, quick_gelu=False, out=None, **k):
+        y = a.float() @ w.float().t()
+        if bias is not None:
+            y = y + bias.float()
+        if gelu:
+            y = F.gelu(y)
+        if quick_gelu:
+            y = y * torch.sigmoid(1.702 * y)
+        if residual is not None:
+            y = y + residual.float()
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y.half()
+
+    def attention(q, k, v, heads, head_dim, scale=None, causal=False, out=None):
+        B, N, _ = q.shape
+        sp = lambda t: t.float().reshape(B, N, heads, head_dim).transpose(1, 2)
+        o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), is_causal=causal, scale=scale)
+        return o.transpose(1, 2).reshape(B, N, heads * head_dim).half()
+
+    def patchify(x, P, ldk):
+        a = F.unfold(x.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(-1, x.shape[1] * P * P)
+        return F.pad(a, (0, ldk - a.shape[1])).half()
+
+    monkeypatch.setattr(CL.L, "gemm", gemm)
+    monkeypatch.setattr(CL.L, "layernorm", lambda x, g, b, eps=1e-5, out=None:
+                        F.layer_norm(x.float(), (x.shape[-1],), g.float(), b.float(), eps).half())
+    monkeypatch.setattr(CL.L, "encoder_attention", attention)
+    monkeypatch.setattr(CL.L, "patchify", patchify)
+    monkeypatch.setattr(CL.L, "token_embedding",
+                        lambda ids, tok, pos, T: (tok.float()[ids] + pos.float()[torch.arange(ids.numel()) % T]).half())
+    monkeypatch.setattr(CL.L, "skinny_linear", lambda x, w, **k: (x.float() @ w.float().t()).half())
+
+    def rounded(module):
+        with torch.no_grad():
+            for prm in module.parameters():
+                prm.copy_(prm.half().float())          # the tower stores fp16 weights
+        return module.eval()
+
+    def close(a, b, tol=1e-2):
+        return (a.float() - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+    torch.manual_seed(0)
+    vc = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=2, image_size=28,
+                          patch_size=14, projection_dim=32, hidden_act="gelu")
+    m = rounded(CLIPVisionModelWithProjection(vc))
+    t = CL.ClipTower(m.state_dict(), vc, "vision", "cpu")
+    x = torch.randn(2, 3, 28, 28).half()
+    with torch.no_grad():
+        ref = m(x.float(), output_hidden_states=True)
+    full = t.vision_forward(x, output_hidden_states=True)
+    assert len(full.hidden_states) == 4 == len(ref.hidden_states)
+    assert all(close(a, b) for a, b in zip(full.hidden_states, ref.hidden_states))
+    assert close(t.vision_hidden(x, -2), ref.hidden_states[-2]) and not close(t.vision_hidden(x, -2), ref.hidden_states[-1])
+    assert close(full.image_embeds, ref.image_embeds)
+    with pytest.raises(ValueError, match="patches"):
+        t.vision_hidden(torch.zeros(1, 3, 42, 42).half())
+    for eos in (2, 99):                      # legacy argmax pooling / first-EOS pooling
+        tc = CLIPTextConfig(vocab_size=100, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=1,
+                            max_position_embeddings=16, projection_dim=32, hidden_act="quick_gelu", eos_token_id=eos,
+                            bos_token_id=0, pad_token_id=1)
+        tm = rounded(CLIPTextModelWithProjection(tc))
+        tt = CL.ClipTower(tm.state_dict(), tc, "text", "cpu")
+        ids = torch.randint(3, 98, (3, 16))
+        ids[0, 5], ids[1, 9], ids[2, 15] = 99, 99, 99
+        ids[0, 6:] = 1
+        with torch.no_grad():
+            tr = tm(ids, output_hidden_states=True)
+        to = tt.text_forward(ids)
+        assert len(to.hidden_states) == 3 and all(close(a, b) for a, b in zip(to.hidden_states, tr.hidden_states))
+        assert close(to.last_hidden_state, tr.last_hidden_state) and close(to.text_embeds, tr.text_embeds, 2e-2)
+
+
 def test_product_does_not_import_oracle():
     """The product path must never route through the oracle or any CPU fallback."""
     pkg = os.path.join(ROOT, "idm-vton_b200")
