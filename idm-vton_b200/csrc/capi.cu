@@ -11,8 +11,11 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
                  const void* temb, long long ld_temb, const void* sc0, int C0, const void* sc1, int C1, const void* w_sc,
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
                  int stride, cudaStream_t stream);
-int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
-                     cudaStream_t stream);
+int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                     const void* residual, void* out, cudaStream_t stream);
+int split_tf32_impl(const void* x, long long stride_b, int B, long long per_batch, float scale, void* hi, void* lo,
+                    cudaStream_t stream);
+int softmax_split_tf32_impl(const void* s, long long rows, int N, void* phi, void* plo, cudaStream_t stream);
 int groupnorm_f32_impl(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps, int silu,
                        void* stats_ws, long long stats_ws_doubles, void* out, cudaStream_t stream);
 int cross_attn_impl(const void* q, long long ldq, const void* kt, const void* vt, long long ldkv_t, int Nt,
@@ -55,7 +58,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
 
 extern "C" {
 
-int b200vton_version(void) { return 104; }
+int b200vton_version(void) { return 105; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
@@ -130,8 +133,15 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
 }
 
 int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
-                               void* out, void* stream) {
-  return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, out, S(stream));
+                               const void* residual, void* out, void* stream) {
+  return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, residual, out, S(stream));
+}
+int b200vton_split_tf32(const void* x, int64_t stride_b, int B, int64_t per_batch, float scale, void* hi, void* lo,
+                        void* stream) {
+  return vton::split_tf32_impl(x, stride_b, B, per_batch, scale, hi, lo, S(stream));
+}
+int b200vton_softmax_split_tf32(const void* scores, int64_t rows, int N, void* p_hi, void* p_lo, void* stream) {
+  return vton::softmax_split_tf32_impl(scores, rows, N, p_hi, p_lo, S(stream));
 }
 
 int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps,

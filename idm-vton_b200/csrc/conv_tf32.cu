@@ -10,7 +10,7 @@
 // padding), weights [9][Cout][Cin] fp32, a cluster of two CTAs per 256 x BN tile (each CTA stages its 128 pixels and
 // half of the weight tile per 32-channel slab; 128-byte smem rows, SWIZZLE_128B), `tcgen05.mma.cta_group::2.kind::tf32`
 // (K = 8 per instruction), fp32 accumulators double-buffered in TMEM, persistent tile loop.
-//   warp 0: TMA producer   warp 1: MMA issuer (leader) + TMEM alloc   warps 2..9: epilogue (acc + bias -> 32x32 fp32
+//   warp 0: TMA producer   warp 1: MMA issuer (leader) + TMEM alloc   warps 2..9: epilogue (acc + bias (+ residual) -> 32x32 fp32
 //   chunk staged in 128B-swizzled smem -> TMA store; rows/channels outside the tensor are clipped by the map)
 #include "common.cuh"
 #include "gemm_common.cuh"
@@ -20,6 +20,7 @@ namespace vton {
 
 struct ConvF32Params {
   const float* bias;     // [Cout] or null
+  const float* residual; // [B,H,W,Cout] fp32 NHWC or null: out = (acc + bias) + residual (the resnet's `x + h`)
   int B, H, W, Cout;
   int bw, bh, bb;        // pixel box of a 128-row tile (bw*bh*bb == 128)
   int tiles_x, tiles_y;
@@ -182,6 +183,14 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      // this thread's accumulator row = pixel (x0 + lx, y0 + ly, b0 + lb) of the tile's box (c fastest, then x, y, b)
+      const float* res_row = nullptr;
+      if (p.residual != nullptr) {
+        const int r_local = quarter * 32 + lane;
+        const int px = x0 + r_local % p.bw, py = y0 + (r_local / p.bw) % p.bh, pb = b0 + r_local / (p.bw * p.bh);
+        if (px < p.W && py < p.H && pb < p.B)
+          res_row = p.residual + ((static_cast<long long>(pb) * p.H + py) * p.W + px) * p.Cout;
+      }
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
         uint32_t v[32];
@@ -197,6 +206,18 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[g * 4 + 1] = __float_as_uint(__uint_as_float(v[g * 4 + 1]) + b4.y);
               v[g * 4 + 2] = __float_as_uint(__uint_as_float(v[g * 4 + 2]) + b4.z);
               v[g * 4 + 3] = __float_as_uint(__uint_as_float(v[g * 4 + 3]) + b4.w);
+            }
+          }
+        }
+        if (res_row != nullptr) {   // after the bias rounding, like torch's `x + conv(h)`
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (ncol + g * 4 < p.Cout) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(res_row + ncol + g * 4));
+              v[g * 4 + 0] = __float_as_uint(__uint_as_float(v[g * 4 + 0]) + r4.x);
+              v[g * 4 + 1] = __float_as_uint(__uint_as_float(v[g * 4 + 1]) + r4.y);
+              v[g * 4 + 2] = __float_as_uint(__uint_as_float(v[g * 4 + 2]) + r4.z);
+              v[g * 4 + 3] = __float_as_uint(__uint_as_float(v[g * 4 + 3]) + r4.w);
             }
           }
         }
@@ -257,9 +278,10 @@ static int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return kOk;
 }
 
-// x: [B,H,W,Cin] fp32 NHWC (dense), w: [9][Cout][Cin] fp32 (tap-major), bias: [Cout] fp32 or null, out: [B,H,W,Cout]
-int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias, void* out,
-                     cudaStream_t stream) {
+// x: [B,H,W,Cin] fp32 NHWC (dense), w: [9][Cout][Cin] fp32 (tap-major), bias: [Cout] fp32 or null, residual: [B,H,W,Cout]
+// fp32 NHWC or null (added after the bias), out: [B,H,W,Cout]
+int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                     const void* residual, void* out, cudaStream_t stream) {
   VTON_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv3x3_f32: empty input");
   VTON_CHECK_ARG(Cin % 32 == 0 && Cout % 32 == 0 && Cout >= 64, "conv3x3_f32: Cin=%d / Cout=%d must be multiples of 32 (Cout >= 64)", Cin, Cout);
   VTON_CHECK_ARG(x && w && out, "conv3x3_f32: null pointer");
@@ -296,6 +318,7 @@ int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w,
   }
   ConvF32Params p{};
   p.bias = static_cast<const float*>(bias);
+  p.residual = static_cast<const float*>(residual);
   p.B = B;
   p.H = H;
   p.W = W;

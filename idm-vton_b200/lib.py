@@ -25,7 +25,9 @@ SIGNATURES = {
     "b200vton_encoder_attention": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _i, _vp],
     "b200vton_patchify": [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "b200vton_token_embedding": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
-    "b200vton_conv3x3_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
+    "b200vton_conv3x3_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
+    "b200vton_split_tf32": [_vp, _i64, _i, _i64, _f, _vp, _vp, _vp],
+    "b200vton_softmax_split_tf32": [_vp, _i64, _i, _vp, _vp, _vp],
     "b200vton_groupnorm_nhwc_f32": [_vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i64, _vp, _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
@@ -41,7 +43,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 104      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
+ABI_VERSION = 105      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
 
 
 def load(build_if_missing=True):
@@ -256,18 +258,49 @@ def pack_conv3x3_f32(weight):
     return weight.detach().permute(2, 3, 0, 1).reshape(9, weight.shape[0], weight.shape[1]).contiguous()
 
 
-def conv3x3_f32(x, w_packed, bias=None):
-    """x: logical [B,Cin,H,W] fp32 (any strides; converted to channels_last = NHWC memory); returns a channels_last
-    [B,Cout,H,W] fp32 tensor."""
+def conv3x3_f32(x, w_packed, bias=None, residual=None):
+    """x: logical [B,Cin,H,W] fp32 (any strides; converted to channels_last = NHWC memory); residual: logical [B,Cout,H,W]
+    fp32 or None, added after the bias in the epilogue; returns a channels_last [B,Cout,H,W] fp32 tensor."""
     lib = load()
     B, Cin, H, W = x.shape
     Cout = w_packed.shape[1]
     assert w_packed.dtype == torch.float32 and w_packed.is_contiguous() and w_packed.shape == (9, Cout, Cin)
     x = x.contiguous(memory_format=torch.channels_last)
+    if residual is not None:
+        assert residual.shape == (B, Cout, H, W) and residual.dtype == torch.float32
+        residual = residual.contiguous(memory_format=torch.channels_last)
     out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-    rc = lib.b200vton_conv3x3_nhwc_f32(_p(x), B, H, W, Cin, _p(w_packed), Cout, _p(bias), _p(out), _stream())
+    rc = lib.b200vton_conv3x3_nhwc_f32(_p(x), B, H, W, Cin, _p(w_packed), Cout, _p(bias), _p(residual), _p(out), _stream())
     _check(rc, "b200vton_conv3x3_nhwc_f32")
     return out
+
+
+def split_tf32(x, scale=1.0):
+    """x: fp32 [B, ...] whose per-batch block is contiguous (a dense tensor or a row slice x[:, a:b] of a dense [B,N,C] one).
+    Returns dense (hi, lo) with hi = tf32(x*scale), lo = tf32(x*scale - hi)."""
+    lib = load()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2
+    B = x.shape[0]
+    per = x[0].numel()
+    if not x[0].is_contiguous():
+        x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    lo = torch.empty_like(hi)
+    rc = lib.b200vton_split_tf32(_p(x), x.stride(0) if B > 1 else per, B, per, float(scale), _p(hi), _p(lo), _stream())
+    _check(rc, "b200vton_split_tf32")
+    return hi, lo
+
+
+def softmax_split_tf32(scores):
+    """scores: dense fp32 [..., N]; returns (p_hi, p_lo), the TF32 parts of softmax(scores, -1)."""
+    lib = load()
+    assert scores.is_cuda and scores.dtype == torch.float32 and scores.is_contiguous()
+    N = scores.shape[-1]
+    hi = torch.empty_like(scores)
+    lo = torch.empty_like(scores)
+    rc = lib.b200vton_softmax_split_tf32(_p(scores), scores.numel() // N, N, _p(hi), _p(lo), _stream())
+    _check(rc, "b200vton_softmax_split_tf32")
+    return hi, lo
 
 
 _gn32_ws = {}

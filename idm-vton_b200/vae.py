@@ -50,7 +50,16 @@ def _conv_device_ok(x):
     return x.is_cuda
 
 
-def _conv(conv, x):
+# Round 2, last step: the resnets' residual add rides in the convolution's epilogue (bit-identical: fp32 (acc + bias) + x) and
+# the mid-block attention's split operands / probabilities come from one-pass kernels (`b200vton_split_tf32`,
+# `b200vton_softmax_split_tf32`) with the three score products folded into ONE GEMM over a 3x-long contraction; the ATen
+# formulation measured at a fifth of the VAE's time (profiles/r2_vae_kernel_shares.json). B200VTON_VAE_FUSED=0 /
+# B200VTON_VAE_ATTN_FUSED=0 restore the ATen formulations.
+_ENGINE_FUSED = os.environ.get("B200VTON_VAE_FUSED", "1") == "1"                 # residual add in the convolution's epilogue
+_ATTN_FUSED = os.environ.get("B200VTON_VAE_ATTN_FUSED", "1") == "1"           # one-pass split / softmax-split kernels
+
+
+def _conv(conv, x, residual=None):
     """3x3 / stride 1 / pad 1 fp32 convolutions with 32-aligned channel counts run on the engine's TF32 tensor-core
     kernel on CUDA (`b200vton_conv3x3_nhwc_f32`: TF32 products, fp32 accumulation — the arithmetic class cuDNN uses for
     fp32 convolutions under torch's default `allow_tf32`); every other case (CPU, fp16, conv_in / conv_out with 3-8
@@ -65,8 +74,10 @@ def _conv(conv, x):
             if cache is None or cache[0] != key:
                 cache = (key, L.pack_conv3x3_f32(conv.weight))
                 conv._b200_packed = cache
-            return L.conv3x3_f32(x, cache[1], conv.bias)
-    return conv(x)
+            if residual is not None and not _ENGINE_FUSED:
+                return residual + L.conv3x3_f32(x, cache[1], conv.bias)
+            return L.conv3x3_f32(x, cache[1], conv.bias, residual=residual)
+    return conv(x) if residual is None else residual + conv(x)
 
 
 class _Resnet(nn.Module):
@@ -80,10 +91,9 @@ class _Resnet(nn.Module):
 
     def forward(self, x):
         h = _conv(self.conv1, _gn(self.norm1, x, True))
-        h = _conv(self.conv2, _gn(self.norm2, h, True))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
-        return x + h
+        return _conv(self.conv2, _gn(self.norm2, h, True), residual=x)        # x + conv2(...)
 
 
 def _split_tf32(x):
@@ -109,6 +119,20 @@ def _attention_fp32_3xtf32(q, k, v, chunk=2048):
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
+        if _ATTN_FUSED and q.is_cuda and N % 4 == 0 and C % 4 == 0:
+            from . import lib as L
+            kh, kl = L.split_tf32(k)
+            vh, vl = L.split_tf32(v)
+            k3_t = torch.cat([kh, kl, kh], dim=2).transpose(1, 2)      # [B, 3C, N]: contraction order = small terms first
+            del kh, kl
+            out = torch.empty_like(q)
+            for c0 in range(0, N, chunk):
+                qh, ql = L.split_tf32(q[:, c0:c0 + chunk], scale=C ** -0.5)
+                s = torch.bmm(torch.cat([ql, qh, qh], dim=2), k3_t)    # ql.kh + qh.kl + qh.kh in ONE pass over the scores
+                ph, pl = L.softmax_split_tf32(s)
+                del s
+                out[:, c0:c0 + chunk] = torch.baddbmm(torch.baddbmm(torch.bmm(pl, vh), ph, vl), ph, vh)
+            return out
         kh, kl = _split_tf32(k)
         vh, vl = _split_tf32(v)
         kh_t, kl_t = kh.transpose(1, 2), kl.transpose(1, 2)

@@ -100,9 +100,21 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
  * fp32 out — the arithmetic class PyTorch uses for fp32 cuDNN convolutions by default): the VAE's convolutions
  * (diffusers AutoencoderKL ResnetBlock2D.conv1/conv2, Upsample2D.conv; the reference runs the SDXL VAE in fp32,
  * src/tryon_pipeline.py:913-915,1076-1093). x: [B,H,W,Cin] dense NHWC (= channels_last memory), w: [9][Cout][Cin]
- * (tap-major), bias: [Cout] or NULL, out: [B,H,W,Cout]. Cin, Cout multiples of 32, Cout >= 64, W divisible by 8. */
+ * (tap-major), bias: [Cout] or NULL, residual: [B,H,W,Cout] fp32 NHWC or NULL — out = (acc + bias) + residual, the
+ * ResnetBlock2D's `input_tensor + hidden_states` in the epilogue with torch's rounding; out: [B,H,W,Cout].
+ * Cin, Cout multiples of 32, Cout >= 64, W divisible by 8. */
 int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
-                               void* out, void* stream);
+                               const void* residual, void* out, void* stream);
+
+/* Split operands for fp32-accurate products on the TF32 tensor cores (the VAE mid-block attention, diffusers AutoencoderKL
+ * mid_block.attentions[0], exact fp32 in the reference: src/tryon_pipeline.py:913-915,1076-1093):
+ * hi = tf32(x * scale), lo = tf32(x * scale - hi), both exactly representable in TF32 (10 mantissa bits, round half up).
+ * x: B blocks of per_batch contiguous floats with batch stride stride_b (elements); hi / lo: dense [B, per_batch]. */
+int b200vton_split_tf32(const void* x, int64_t stride_b, int B, int64_t per_batch, float scale, void* hi, void* lo,
+                        void* stream);
+/* Row softmax of fp32 scores [rows, N] (max-subtracted, expf, fp32 sum) written directly as the two TF32 parts of the
+ * probabilities: p_hi = tf32(p), p_lo = tf32(p - p_hi); the fp32 probabilities themselves are never stored. N % 4 == 0. */
+int b200vton_softmax_split_tf32(const void* scores, int64_t rows, int N, void* p_hi, void* p_lo, void* stream);
 
 /* fp32 GroupNorm(32 groups)(+SiLU) over dense NHWC [B,HW,C] fp32 — the VAE's norms (diffusers AutoencoderKL
  * ResnetBlock2D.norm1/norm2 + SiLU, Attention.group_norm, conv_norm_out), deterministic two-stage statistics.

@@ -631,8 +631,10 @@ def test_library_options_and_argument_checks_without_gpu():
     rc = l.b200vton_cross_attention(None, 64, None, None, 64, 77, None, None, 64, 17, None, 64, 1, 1, 128, 0.125, 1.0, None)
     assert rc == 1
     # fp32/TF32 convolution: channel alignment
-    rc = l.b200vton_conv3x3_nhwc_f32(None, 1, 16, 16, 48, None, 64, None, None, None)
+    rc = l.b200vton_conv3x3_nhwc_f32(None, 1, 16, 16, 48, None, 64, None, None, None, None)
     assert rc == 1 and b"multiples of 32" in l.b200vton_last_error()
+    assert l.b200vton_split_tf32(None, 6, 1, 6, 1.0, None, None, None) == 1 and b"split_tf32" in l.b200vton_last_error()
+    assert l.b200vton_softmax_split_tf32(None, 4, 6, None, None, None) == 1
 
 
 def test_vae_conv_dispatch_and_weight_packing_on_cpu():
@@ -664,11 +666,16 @@ def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
         y = torch.nn.functional.silu(y) if silu else y
         return y.contiguous(memory_format=torch.channels_last)
 
-    def fake_conv(x, w_packed, bias=None):
+    def fake_conv(x, w_packed, bias=None, residual=None):
         cout, cin = w_packed.shape[1], w_packed.shape[2]
         w = w_packed.reshape(3, 3, cout, cin).permute(2, 3, 0, 1)
-        return torch.nn.functional.conv2d(x, w, bias, padding=1).contiguous(memory_format=torch.channels_last)
+        y = torch.nn.functional.conv2d(x, w, bias, padding=1)
+        if residual is not None:                       # the kernel's epilogue: (acc + bias) + residual
+            calls["residual"] += 1
+            y = y + residual
+        return y.contiguous(memory_format=torch.channels_last)
 
+    calls = {"conv": 0, "residual": 0}
     torch.manual_seed(0)
     vae = V.AutoencoderKL(block_out_channels=(32, 64), layers_per_block=1).eval()
     x = torch.rand(2, 3, 32, 24) * 2 - 1
@@ -682,17 +689,17 @@ def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
         monkeypatch.setattr(lib, "conv3x3_f32", fake_conv)
         monkeypatch.setattr(lib, "conv3x3_f32_supported", lambda t, cin, cout: cin % 32 == 0 and cout % 32 == 0 and cout >= 64)
         monkeypatch.setattr(V, "_conv_device_ok", lambda t: True)
-        calls = {"conv": 0}
         real_fake = fake_conv
 
-        def counting_conv(x, w_packed, bias=None):
+        def counting_conv(x, w_packed, bias=None, residual=None):
             calls["conv"] += 1
-            return real_fake(x, w_packed, bias)
+            return real_fake(x, w_packed, bias, residual)
 
         monkeypatch.setattr(lib, "conv3x3_f32", counting_conv)
         got_mean = vae.encode(x).latent_dist.mean
         got_img = vae.decode(z).sample
     assert calls["conv"] > 0, "the engine-convolution route was not taken"
+    assert calls["residual"] > 0, "the resnets' residual add did not ride in the convolution's epilogue"
     assert got_mean.shape == ref_mean.shape and got_img.shape == ref_img.shape and got_img.is_contiguous()
     assert (got_mean - ref_mean).abs().max() < 1e-4
     assert (got_img - ref_img).abs().max() < 1e-4

@@ -584,6 +584,12 @@ def test_conv3x3_fp32_tf32(lib, B, Cin, Cout, H, W):
     with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=True):
         e_cudnn = close(torch.nn.functional.conv2d(x, w, b, padding=1), ref, tol=2e-3)
     print(f"tf32 conv err vs fp32: ours {e_ours:.2e}, cuDNN-TF32 {e_cudnn:.2e}")
+    # the resnet's residual add in the epilogue: (acc + bias) + residual in fp32 = what `residual + conv(x)` computes, bit for bit
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+    fused = lib.conv3x3_f32(x, lib.pack_conv3x3_f32(w), b, residual=res)
+    assert torch.equal(fused, res + out)
+    res_nchw = res.contiguous()                    # any strides are accepted (converted to channels_last)
+    assert torch.equal(lib.conv3x3_f32(x, lib.pack_conv3x3_f32(w), b, residual=res_nchw), fused)
 
 
 @pytest.mark.parametrize("B,C,H,W,silu", [(2, 128, 64, 48, True), (1, 256, 37, 24, True), (2, 512, 16, 12, False),
@@ -659,6 +665,49 @@ def test_conv3x3_stride2_downsample(lib, B, H, W, Cin, Cout):
     close(out, ref)
     old = lib.gemm(lib.im2col3x3_s2(x), pack_conv3x3_s2(w), bias=b).view_as(out)
     close(out, old, tol=1e-3)
+
+
+def test_split_tf32_and_softmax_split_kernels(lib):
+    """b200vton_split_tf32 == the ATen formulation of vae._split_tf32 bit for bit (dense and row-sliced inputs, with a scale);
+    b200vton_softmax_split_tf32: both parts TF32-representable, hi + lo = softmax to 2^-22, softmax itself at fp32 accuracy."""
+    from idm_vton_b200.vae import _split_tf32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(3, 1000, 512, device="cuda", generator=g) * 7
+    hi, lo = lib.split_tf32(x)
+    rh, rl = _split_tf32(x)
+    assert torch.equal(hi, rh) and torch.equal(lo, rl)
+    sl = x[:, 100:356]                                  # what the attention passes per query chunk
+    hi, lo = lib.split_tf32(sl, scale=512 ** -0.5)
+    rh, rl = _split_tf32(sl * 512 ** -0.5)
+    assert hi.is_contiguous() and torch.equal(hi, rh) and torch.equal(lo, rl)
+    assert not (hi.view(torch.int32) & 8191).any() and not (lo.view(torch.int32) & 8191).any()
+    for rows, N in ((64, 12288), (7, 3072), (5, 4)):
+        s = torch.randn(2, rows, N, device="cuda", generator=g) * 4
+        ph, pl = lib.softmax_split_tf32(s)
+        p64 = torch.softmax(s.double(), -1)
+        p32 = torch.softmax(s, -1)
+        assert not (ph.view(torch.int32) & 8191).any() and not (pl.view(torch.int32) & 8191).any()
+        e_kernel = ((ph.double() + pl.double()) - p64).abs().max().item()
+        e_torch = (p32.double() - p64).abs().max().item()
+        print(f"softmax_split rows {rows} N {N}: |hi+lo - fp64| {e_kernel:.2e}, torch fp32 softmax {e_torch:.2e}")
+        assert e_kernel <= 4 * e_torch + 3e-7 * p64.max().item()
+        assert ((ph.double() + pl.double()).sum(-1) - 1).abs().max().item() < 1e-5
+
+
+def test_vae_attention_fused_equals_aten_formulation(monkeypatch):
+    """The one-pass kernels + the 3x-long contraction against the ATen formulation of the same 3xTF32 attention."""
+    import idm_vton_b200.vae as V
+    g = torch.Generator(device="cuda").manual_seed(10)
+    B, N, C = 2, 3072, 512
+    q, k, v = (torch.randn(B, N, C, device="cuda", generator=g) * s for s in (1.5, 1.5, 1.0))
+    ref = F.scaled_dot_product_attention(q[:, None].double(), k[:, None].double(), v[:, None].double())[:, 0]
+    monkeypatch.setattr(V, "_ATTN_FUSED", True)
+    o_f = V._attention_fp32_3xtf32(q, k, v, chunk=1024)
+    monkeypatch.setattr(V, "_ATTN_FUSED", False)
+    o_a = V._attention_fp32_3xtf32(q, k, v, chunk=1024)
+    e_f, e_a = ((x.double() - ref).abs().max().item() for x in (o_f, o_a))
+    print(f"VAE attention vs fp64: fused {e_f:.2e}, ATen formulation {e_a:.2e}, fused vs ATen {(o_f - o_a).abs().max().item():.2e}")
+    assert e_f <= 2 * e_a + 1e-6
 
 
 def test_vae_attention_3xtf32_matches_fp32_sdpa():
