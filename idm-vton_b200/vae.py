@@ -6,8 +6,9 @@ force_upcast,latent_channels,block_out_channels}` (:911-932,1646,1868-1880). dif
 this module supplies an architecture-compatible VAE (same parameter names as diffusers 0.25.0's AutoencoderKL, restated
 from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): on a GPU
 the fp32 VAE runs NHWC with its 3x3 / stride-1 convolutions on `b200vton_conv3x3_nhwc_f32` (TF32 tcgen05) and every
-GroupNorm(+SiLU) on `b200vton_groupnorm_nhwc_f32` (default ON, see `_ENGINE_NHWC`); the mid-block attention is a split-TF32
-formulation on cuBLAS; resampling, the stride-2 / 3-8-channel / 1x1 convolutions and the residual adds are PyTorch.
+GroupNorm(+SiLU) on `b200vton_groupnorm_nhwc_f32` (default ON, see `_ENGINE_NHWC`), the resnets' residual add rides in the
+convolution's epilogue, the mid-block attention is a split-TF32 formulation (cuBLAS GEMMs between this library's one-pass split /
+softmax kernels); resampling and the stride-2 / 3-8-channel / 1x1 convolutions are PyTorch.
 """
 import os
 import types
@@ -114,7 +115,11 @@ def _attention_fp32_3xtf32(q, k, v, chunk=2048):
     removes the TF32 operand rounding (the dropped a_lo·b_lo term is 2^-22 relative); what remains is the tensor core's own
     fp32 accumulation over thousands of keys: 3.9e-5 max abs error against fp64 at 3072 keys where fp32 SDPA has 3.6e-6
     and a single TF32 pass 3.0e-3 (tests/test_kernels_gpu.py) — an order below the error of the TF32 convolutions around
-    it. Queries are processed in chunks so the score block stays small. Plain torch.matmul (cuBLAS): host-side plumbing of a SURVEY 8f row, not the hot path."""
+    it. Queries are processed in chunks so the score block stays small. The products are cuBLAS TF32 GEMMs; the split operands and
+    the softmax come from `b200vton_split_tf32` / `b200vton_softmax_split_tf32` (one pass each; the three score products are ONE
+    GEMM over the concatenated contraction [q_lo | q_hi | q_hi] . [k_hi | k_lo | k_hi]^T, small terms first), which took the
+    VAE from 125.2 to 110.7 ms per (6-image encode + 2-image decode) on B200; `_ATTN_FUSED = False` is the ATen formulation
+    of the same arithmetic (kept as the cross-check of tests/test_kernels_gpu.py). Host-side plumbing of a SURVEY 8f row."""
     B, N, C = q.shape
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
