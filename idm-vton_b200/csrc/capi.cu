@@ -12,12 +12,12 @@ int conv3x3_impl(const void* x, long long ldx, int B, int H, int W, int Cin, con
                  const void* bias_sc, const void* residual, long long ldr, void* out, long long ldo, int force_bn,
                  int stride, cudaStream_t stream);
 int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
-                     const void* residual, void* out, cudaStream_t stream);
+                     const void* residual, void* out, int in_fp16, cudaStream_t stream);
 int split_tf32_impl(const void* x, long long stride_b, int B, long long per_batch, float scale, void* hi, void* lo,
                     cudaStream_t stream);
 int softmax_split_tf32_impl(const void* s, long long rows, int N, void* phi, void* plo, cudaStream_t stream);
 int groupnorm_f32_impl(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps, int silu,
-                       void* stats_ws, long long stats_ws_doubles, void* out, cudaStream_t stream);
+                       void* stats_ws, long long stats_ws_doubles, void* out, int out_fp16, cudaStream_t stream);
 int cross_attn_impl(const void* q, long long ldq, const void* kt, const void* vt, long long ldkv_t, int Nt,
                     const void* ki, const void* vi, long long ldkv_i, int Ni, void* out, long long ldo, int B, int H,
                     int Nq, float scale, float ip_scale, cudaStream_t stream);
@@ -58,7 +58,7 @@ int cfg_ddpm_impl(const void* eps, int ldc, int B, int C, int H, int W, const vo
 
 extern "C" {
 
-int b200vton_version(void) { return 105; }
+int b200vton_version(void) { return 106; }
 const char* b200vton_last_error(void) { return vton::get_last_error(); }
 long long b200vton_launch_count(void) { return vton::launch_count(); }
 int b200vton_set_option(const char* name, int value) {
@@ -134,7 +134,11 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
 
 int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                                const void* residual, void* out, void* stream) {
-  return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, residual, out, S(stream));
+  return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, residual, out, 0, S(stream));
+}
+int b200vton_conv3x3_nhwc_f16in_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                                    const void* residual, void* out, void* stream) {
+  return vton::conv3x3_f32_impl(x, B, H, W, Cin, w, Cout, bias, residual, out, 1, S(stream));
 }
 int b200vton_split_tf32(const void* x, int64_t stride_b, int B, int64_t per_batch, float scale, void* hi, void* lo,
                         void* stream) {
@@ -145,8 +149,8 @@ int b200vton_softmax_split_tf32(const void* scores, int64_t rows, int N, void* p
 }
 
 int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps,
-                                 int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, void* stream) {
-  return vton::groupnorm_f32_impl(x, B, HW, C, gamma, beta, eps, silu, stats_ws, stats_ws_doubles, out, S(stream));
+                                 int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, int out_fp16, void* stream) {
+  return vton::groupnorm_f32_impl(x, B, HW, C, gamma, beta, eps, silu, stats_ws, stats_ws_doubles, out, out_fp16, S(stream));
 }
 
 int b200vton_groupnorm(const void* x0, int C0, const void* x1, int C1, int B, int HW, const void* gamma,

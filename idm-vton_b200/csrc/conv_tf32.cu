@@ -58,10 +58,14 @@ __device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t d_tmem, uint64_t a_des
       : "memory");
 }
 
-template <int BN, int STAGES>
+// F16IN: activations and weights arrive as fp16 (64 channels per 128-byte slab row, kind::f16 MMAs at twice the TF32 rate);
+// accumulators, bias, residual and output stay fp32. The fp16 operand has the 10-bit mantissa TF32 would round an fp32 operand
+// to, so the arithmetic class is the same; the producer is the VAE's GroupNorm(+SiLU) storing fp16 (norm_f32.cu, HALF_OUT).
+template <int BN, int STAGES, bool F16IN>
 __global__ void __launch_bounds__(320, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvF32Params p, int m_pairs) {
+  constexpr int BK = F16IN ? 64 : CT_BK;   // channels per slab (128 bytes)
   using L = SmemT<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -126,7 +130,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_dst = a_dst + CT_A_BYTES;
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
           const int tap = s / p.cin_slabs;
-          const int c0 = (s - tap * p.cin_slabs) * CT_BK;
+          const int c0 = (s - tap * p.cin_slabs) * BK;
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
           tma2_load_4d(a_dst, &tmA, full_bar(stage), c0, x0 + dx, y0 + dy, b0);
           tma2_load_2d(b_dst, &tmB, full_bar(stage), c0, tap * p.Cout + n0);
@@ -135,7 +139,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(256, BN);
+      constexpr uint32_t idesc = F16IN ? make_idesc_f16(256, BN, 0) : make_idesc_tf32(256, BN);
       uint32_t it = 0;
       int tile_iter = 0;
       for (int t = cluster_id; t < total_tiles; t += n_clusters, ++tile_iter) {
@@ -152,10 +156,11 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_src = smem_base + stage * L::STAGE_BYTES;
           const uint32_t b_src = a_src + CT_A_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 8 tf32 = 32 bytes per MMA step
+          for (int k = 0; k < 4; ++k) {   // 8 tf32 (or 16 halves) = 32 bytes per MMA step
             const uint64_t a_desc = make_smem_desc_sw128(a_src + k * 32, 0, 1024);
             const uint64_t b_desc = make_smem_desc_sw128(b_src + k * 32, 0, 1024);
-            tc_mma_tf32_2cta(d, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            if (F16IN) tc_mma_f16_2cta(d, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            else tc_mma_tf32_2cta(d, a_desc, b_desc, idesc, (s > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit_2cta(empty_bar(stage), 0x3);
         }
@@ -249,11 +254,11 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F16IN>
 static int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const ConvF32Params& p,
                        int m_pairs, cudaStream_t stream) {
   using L = SmemT<BN, STAGES>;
-  auto kern = conv_tf32_kernel<BN, STAGES>;
+  auto kern = conv_tf32_kernel<BN, STAGES, F16IN>;
   static bool configured = false;
   if (!configured) {
     VTON_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -280,10 +285,14 @@ static int launch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 // x: [B,H,W,Cin] fp32 NHWC (dense), w: [9][Cout][Cin] fp32 (tap-major), bias: [Cout] fp32 or null, residual: [B,H,W,Cout]
 // fp32 NHWC or null (added after the bias), out: [B,H,W,Cout]
+// in_fp16: x and w are fp16 (same layouts), Cin a multiple of 64; everything else stays fp32.
 int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
-                     const void* residual, void* out, cudaStream_t stream) {
+                     const void* residual, void* out, int in_fp16, cudaStream_t stream) {
   VTON_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv3x3_f32: empty input");
   VTON_CHECK_ARG(Cin % 32 == 0 && Cout % 32 == 0 && Cout >= 64, "conv3x3_f32: Cin=%d / Cout=%d must be multiples of 32 (Cout >= 64)", Cin, Cout);
+  VTON_CHECK_ARG(!in_fp16 || Cin % 64 == 0, "conv3x3_f32: fp16 operands need Cin=%d to be a multiple of 64", Cin);
+  const int esz = in_fp16 ? 2 : 4;          // operand element size
+  const int bk = in_fp16 ? 64 : 32;         // channels per 128-byte slab row
   VTON_CHECK_ARG(x && w && out, "conv3x3_f32: null pointer");
   int bw = 1;
   while (bw < 128 && W % (bw * 2) == 0) bw *= 2;
@@ -295,16 +304,16 @@ int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w,
   CUtensorMap tmA, tmB, tmOut;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
-    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 4, static_cast<uint64_t>(W) * Cin * 4,
-                           static_cast<uint64_t>(H) * W * Cin * 4};
-    uint32_t box[4] = {32, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
-    if (int e = encode_tmap_f32(&tmA, x, 4, dims, strides, box)) return e;
+    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * esz, static_cast<uint64_t>(W) * Cin * esz,
+                           static_cast<uint64_t>(H) * W * Cin * esz};
+    uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+    if (int e = in_fp16 ? encode_tmap_f16(&tmA, x, 4, dims, strides, box) : encode_tmap_f32(&tmA, x, 4, dims, strides, box)) return e;
   }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(9) * Cout};
-    uint64_t strides[1] = {static_cast<uint64_t>(Cin) * 4};
-    uint32_t box[2] = {32, static_cast<uint32_t>(bn / 2)};
-    if (int e = encode_tmap_f32(&tmB, w, 2, dims, strides, box)) return e;
+    uint64_t strides[1] = {static_cast<uint64_t>(Cin) * esz};
+    uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bn / 2)};
+    if (int e = in_fp16 ? encode_tmap_f16(&tmB, w, 2, dims, strides, box) : encode_tmap_f32(&tmB, w, 2, dims, strides, box)) return e;
   }
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
@@ -328,12 +337,16 @@ int conv3x3_f32_impl(const void* x, int B, int H, int W, int Cin, const void* w,
   p.bb = bb;
   p.tiles_x = W / bw;
   p.tiles_y = cdiv(H, bh);
-  p.cin_slabs = Cin / 32;
+  p.cin_slabs = Cin / bk;
   p.n_tiles = cdiv(Cout, bn);
   const int m_tiles = p.tiles_x * p.tiles_y * cdiv(B, bb);
   const int m_pairs = cdiv(m_tiles, 2);
-  if (bn == 256) return launch_tf32<256, 5>(tmA, tmB, tmOut, p, m_pairs, stream);
-  return launch_tf32<128, 6>(tmA, tmB, tmOut, p, m_pairs, stream);
+  if (in_fp16) {
+    if (bn == 256) return launch_tf32<256, 5, true>(tmA, tmB, tmOut, p, m_pairs, stream);
+    return launch_tf32<128, 6, true>(tmA, tmB, tmOut, p, m_pairs, stream);
+  }
+  if (bn == 256) return launch_tf32<256, 5, false>(tmA, tmB, tmOut, p, m_pairs, stream);
+  return launch_tf32<128, 6, false>(tmA, tmB, tmOut, p, m_pairs, stream);
 }
 
 }  // namespace vton

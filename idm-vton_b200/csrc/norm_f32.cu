@@ -64,10 +64,13 @@ gn32_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_cta, 
   }
 }
 
+// HALF_OUT: the normalised (+SiLU) values are stored as fp16 — the consumer is the fp16-operand convolution
+// (conv_tf32.cu, F16IN), whose 10-bit operand mantissa is the one the TF32 convolution would round these values to anyway.
+template <bool HALF_OUT>
 __global__ void __launch_bounds__(GN32_THREADS)
 gn32_apply_kernel(const float* __restrict__ x, int HW, int C, int rows_per_cta, const double* __restrict__ partial,
                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                  float* __restrict__ out) {
+                  void* __restrict__ out_v) {
   const int V = C / 4;
   const int cpg = C / GN32_GROUPS;
   const int row_lanes = GN32_THREADS / V;
@@ -125,13 +128,21 @@ gn32_apply_kernel(const float* __restrict__ x, int HW, int C, int rows_per_cta, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) y[j] = silu_f(y[j]);
     }
-    *reinterpret_cast<float4*>(out + off + r * C) = make_float4(y[0], y[1], y[2], y[3]);
+    if (HALF_OUT) {
+      uint2 o;
+      o.x = pack_h2(y[0], y[1]);
+      o.y = pack_h2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(static_cast<__half*>(out_v) + off + r * C) = o;
+    } else {
+      *reinterpret_cast<float4*>(static_cast<float*>(out_v) + off + r * C) = make_float4(y[0], y[1], y[2], y[3]);
+    }
   }
 }
 
-// x, out: [B, HW, C] fp32 dense NHWC; gamma/beta: [C] fp32 or null; stats_ws: B * chunks(<= 1184) * 64 doubles
+// x: [B, HW, C] fp32 dense NHWC; out: the same shape, fp32 or (out_fp16) fp16; gamma/beta: [C] fp32 or null;
+// stats_ws: B * chunks(<= 1184) * 64 doubles
 int groupnorm_f32_impl(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps, int silu,
-                       void* stats_ws, long long stats_ws_doubles, void* out, cudaStream_t stream) {
+                       void* stats_ws, long long stats_ws_doubles, void* out, int out_fp16, cudaStream_t stream) {
   VTON_CHECK_ARG(B > 0 && HW > 0 && C > 0, "groupnorm_f32: empty input");
   VTON_CHECK_ARG(C % GN32_GROUPS == 0 && C % 4 == 0 && C / 4 <= GN32_THREADS, "groupnorm_f32: C=%d unsupported (32 groups, C <= 2048, C %% 4 == 0)", C);
   VTON_CHECK_ARG(x && out && stats_ws, "groupnorm_f32: null pointer");
@@ -146,10 +157,16 @@ int groupnorm_f32_impl(const void* x, int B, int HW, int C, const void* gamma, c
   dim3 grid(chunks, B);
   gn32_stats_kernel<<<grid, GN32_THREADS, 0, stream>>>(static_cast<const float*>(x), HW, C, rows_per_cta,
                                                        static_cast<double*>(stats_ws));
-  gn32_apply_kernel<<<grid, GN32_THREADS, 0, stream>>>(static_cast<const float*>(x), HW, C, rows_per_cta,
-                                                       static_cast<const double*>(stats_ws),
-                                                       static_cast<const float*>(gamma), static_cast<const float*>(beta),
-                                                       eps, silu, static_cast<float*>(out));
+  if (out_fp16)
+    gn32_apply_kernel<true><<<grid, GN32_THREADS, 0, stream>>>(static_cast<const float*>(x), HW, C, rows_per_cta,
+                                                             static_cast<const double*>(stats_ws),
+                                                             static_cast<const float*>(gamma), static_cast<const float*>(beta),
+                                                             eps, silu, out);
+  else
+    gn32_apply_kernel<false><<<grid, GN32_THREADS, 0, stream>>>(static_cast<const float*>(x), HW, C, rows_per_cta,
+                                                              static_cast<const double*>(stats_ws),
+                                                              static_cast<const float*>(gamma), static_cast<const float*>(beta),
+                                                              eps, silu, out);
   count_launch(2);
   VTON_CUDA(cudaGetLastError());
   return kOk;

@@ -28,7 +28,8 @@ SIGNATURES = {
     "b200vton_conv3x3_nhwc_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "b200vton_split_tf32": [_vp, _i64, _i, _i64, _f, _vp, _vp, _vp],
     "b200vton_softmax_split_tf32": [_vp, _i64, _i, _vp, _vp, _vp],
-    "b200vton_groupnorm_nhwc_f32": [_vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i64, _vp, _vp],
+    "b200vton_groupnorm_nhwc_f32": [_vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i64, _vp, _i, _vp],
+    "b200vton_conv3x3_nhwc_f16in_f32": [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "b200vton_groupnorm": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "b200vton_layernorm": [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _i64, _vp],
     "b200vton_nchw_to_nhwc": [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp],
@@ -43,7 +44,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 105      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
+ABI_VERSION = 106      # must equal b200vton_version() of the loaded library (bumped with every SIGNATURES change)
 
 
 def load(build_if_missing=True):
@@ -306,8 +307,26 @@ def softmax_split_tf32(scores):
 _gn32_ws = {}
 
 
-def groupnorm_f32_nhwc(x, gamma, beta, eps, silu):
-    """x: logical [B,C,H,W] fp32 in channels_last memory (= dense NHWC); returns the same layout."""
+def conv3x3_f16in(x16, w_packed16, bias=None, residual=None):
+    """x16: logical [B,Cin,H,W] fp16 in channels_last memory (the fp16 output of groupnorm_f32_nhwc); w_packed16: [9,Cout,Cin]
+    fp16; bias [Cout] fp32; residual logical [B,Cout,H,W] fp32 or None. Returns a channels_last [B,Cout,H,W] fp32 tensor."""
+    lib = load()
+    B, Cin, H, W = x16.shape
+    Cout = w_packed16.shape[1]
+    assert x16.dtype == torch.float16 and x16.is_contiguous(memory_format=torch.channels_last)
+    assert w_packed16.dtype == torch.float16 and w_packed16.is_contiguous() and w_packed16.shape == (9, Cout, Cin)
+    if residual is not None:
+        assert residual.shape == (B, Cout, H, W) and residual.dtype == torch.float32
+        residual = residual.contiguous(memory_format=torch.channels_last)
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x16.device, memory_format=torch.channels_last)
+    rc = lib.b200vton_conv3x3_nhwc_f16in_f32(_p(x16), B, H, W, Cin, _p(w_packed16), Cout, _p(bias), _p(residual), _p(out),
+                                             _stream())
+    _check(rc, "b200vton_conv3x3_nhwc_f16in_f32")
+    return out
+
+
+def groupnorm_f32_nhwc(x, gamma, beta, eps, silu, out_half=False):
+    """x: logical [B,C,H,W] fp32 in channels_last memory (= dense NHWC); returns the same layout, fp32 or (out_half) fp16."""
     lib = load()
     B, C, H, W = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
@@ -317,9 +336,10 @@ def groupnorm_f32_nhwc(x, gamma, beta, eps, silu):
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.float64, device=x.device)
         _gn32_ws[key] = ws
-    out = torch.empty_like(x, memory_format=torch.channels_last)
+    out = torch.empty(x.shape, dtype=torch.float16 if out_half else torch.float32, device=x.device,
+                      memory_format=torch.channels_last)
     rc = lib.b200vton_groupnorm_nhwc_f32(_p(x), B, H * W, C, _p(gamma), _p(beta), float(eps), int(silu), _p(ws),
-                                         ws.numel(), _p(out), _stream())
+                                         ws.numel(), _p(out), int(out_half), _stream())
     _check(rc, "b200vton_groupnorm_nhwc_f32")
     return out
 

@@ -81,6 +81,31 @@ def _conv(conv, x, residual=None):
     return conv(x) if residual is None else residual + conv(x)
 
 
+# GroupNorm(+SiLU) -> convolution with an fp16 hand-off: the TF32 convolution rounds its fp32 operands to 10 mantissa bits
+# anyway, so the norm stores fp16 (same mantissa; its outputs are O(1-10), far inside fp16's range) and the convolution runs
+# with fp16 operands — half the norm's write and the convolution's read, twice the MMA rate, fp32 accumulation / bias /
+# residual / output as before (`b200vton_conv3x3_nhwc_f16in_f32`). B200VTON_VAE_F16ACT=0 keeps the fp32 hand-off.
+_F16_ACT = os.environ.get("B200VTON_VAE_F16ACT", "1") == "1"
+
+
+def _gn_silu_conv(norm, conv, x, residual=None):
+    """conv(silu(norm(x))) (+ residual): the fp16 hand-off when both kernels take the shapes, else `_conv(conv, _gn(...))`."""
+    if (_F16_ACT and _ENGINE_FUSED and _use_nhwc(x) and norm.num_groups == 32 and x.shape[1] % 64 == 0 and x.shape[1] <= 2048
+            and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and torch.backends.cudnn.allow_tf32):
+        from . import lib as L
+        if L.conv3x3_f32_supported(x, conv.in_channels, conv.out_channels):
+            key = (conv.weight.data_ptr(), conv.weight._version)
+            cache = getattr(conv, "_b200_packed16", None)
+            if cache is None or cache[0] != key:
+                cache = (key, L.pack_conv3x3_f32(conv.weight).to(torch.float16))
+                conv._b200_packed16 = cache
+            h16 = L.groupnorm_f32_nhwc(x.contiguous(memory_format=torch.channels_last), norm.weight, norm.bias, norm.eps, True,
+                                       out_half=True)
+            return L.conv3x3_f16in(h16, cache[1], conv.bias, residual=residual)
+    return _conv(conv, _gn(norm, x, True), residual=residual)
+
+
 class _Resnet(nn.Module):
     def __init__(self, cin, cout):
         super().__init__()
@@ -91,10 +116,10 @@ class _Resnet(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = _conv(self.conv1, _gn(self.norm1, x, True))
+        h = _gn_silu_conv(self.norm1, self.conv1, x)
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
-        return _conv(self.conv2, _gn(self.norm2, h, True), residual=x)        # x + conv2(...)
+        return _gn_silu_conv(self.norm2, self.conv2, h, residual=x)        # x + conv2(silu(norm2(h)))
 
 
 def _split_tf32(x):

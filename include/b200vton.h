@@ -106,6 +106,13 @@ int b200vton_cross_attention(const void* q, int64_t ldq, const void* kt, const v
 int b200vton_conv3x3_nhwc_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
                                const void* residual, void* out, void* stream);
 
+/* The same convolution with fp16 operands: x [B,H,W,Cin] fp16 NHWC (the fp16 output of b200vton_groupnorm_nhwc_f32), w
+ * [9][Cout][Cin] fp16; fp32 accumulation, fp32 bias / residual / out. An fp16 operand carries the 10-bit mantissa the TF32
+ * tensor core rounds an fp32 operand to (and GroupNorm(+SiLU) outputs are far inside fp16's range), so the arithmetic class is
+ * that of the TF32 convolution at half the operand traffic and twice the MMA rate. Cin a multiple of 64. */
+int b200vton_conv3x3_nhwc_f16in_f32(const void* x, int B, int H, int W, int Cin, const void* w, int Cout, const void* bias,
+                                    const void* residual, void* out, void* stream);
+
 /* Split operands for fp32-accurate products on the TF32 tensor cores (the VAE mid-block attention, diffusers AutoencoderKL
  * mid_block.attentions[0], exact fp32 in the reference: src/tryon_pipeline.py:913-915,1076-1093):
  * hi = tf32(x * scale), lo = tf32(x * scale - hi), both exactly representable in TF32 (10 mantissa bits, round half up).
@@ -119,9 +126,10 @@ int b200vton_softmax_split_tf32(const void* scores, int64_t rows, int N, void* p
 /* fp32 GroupNorm(32 groups)(+SiLU) over dense NHWC [B,HW,C] fp32 — the VAE's norms (diffusers AutoencoderKL
  * ResnetBlock2D.norm1/norm2 + SiLU, Attention.group_norm, conv_norm_out), deterministic two-stage statistics.
  * gamma/beta: [C] fp32 or NULL. stats_ws: scratch of stats_ws_doubles doubles, at least 64 * max(B, 1184) is always
- * enough. Validated on B200 in round 2; the VAE's default route (B200VTON_VAE_NHWC=0 restores the cuDNN NCHW path). */
+ * enough. out: fp32, or — out_fp16 != 0 — fp16 of the same shape (one rounding of the fp32 result), the operand format of
+ * b200vton_conv3x3_nhwc_f16in_f32. The VAE's default route (B200VTON_VAE_NHWC=0 restores the cuDNN NCHW path). */
 int b200vton_groupnorm_nhwc_f32(const void* x, int B, int HW, int C, const void* gamma, const void* beta, float eps,
-                                 int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, void* stream);
+                                 int silu, void* stats_ws, int64_t stats_ws_doubles, void* out, int out_fp16, void* stream);
 
 /* GroupNorm(32 groups) over NHWC [B,HW,C0+C1] read from up to two channel-concatenated sources (x1 may be NULL),
  * fp32 statistics (deterministic fixed-order reduction, no atomics on data), optional SiLU, fp16 out [B*HW, C0+C1].

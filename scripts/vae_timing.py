@@ -1,5 +1,5 @@
 """A/B of the VAE's fused pieces on one GPU: encoder pass of 6 images at 1024x768 + decoder pass of 2 latents, device events,
-3 iterations after 1 warm-up, for (residual epilogue, attention kernels) in {on, off}. One JSON line."""
+3 iterations after 1 warm-up, for the residual epilogue / attention kernels / fp16 GroupNorm -> convolution hand-off switched on one after the other. One JSON line."""
 import json
 import os
 import sys
@@ -24,8 +24,9 @@ def run():
 
 
 out, keep = {}, {}
-for name, fused, attn in (("aten", False, False), ("residual_epilogue", True, False), ("fused", True, True)):
-    V._ENGINE_FUSED, V._ATTN_FUSED = fused, attn
+for name, fused, attn, f16 in (("aten", False, False, False), ("residual_epilogue", True, False, False),
+                              ("fused", True, True, False), ("fused_f16_handoff", True, True, True)):
+    V._ENGINE_FUSED, V._ATTN_FUSED, V._F16_ACT = fused, attn, f16
     keep[name] = run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,6 +36,6 @@ for name, fused, attn in (("aten", False, False), ("residual_epilogue", True, Fa
     e1.record()
     torch.cuda.synchronize()
     out[name + "_ms"] = round(e0.elapsed_time(e1) / 3, 2)
-for name in ("residual_epilogue", "fused"):
+for name in ("residual_epilogue", "fused", "fused_f16_handoff"):
     out[name + "_vs_aten_maxdiff"] = [float((a - b).abs().max()) for a, b in zip(keep[name], keep["aten"])]
 print(json.dumps(out))

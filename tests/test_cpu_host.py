@@ -660,11 +660,18 @@ def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
     import idm_vton_b200.vae as V
     from idm_vton_b200 import lib
 
-    def fake_gn(x, gamma, beta, eps, silu):
+    def fake_gn(x, gamma, beta, eps, silu, out_half=False):
         assert x.is_contiguous(memory_format=torch.channels_last)
         y = torch.nn.functional.group_norm(x, 32, gamma, beta, eps)
         y = torch.nn.functional.silu(y) if silu else y
-        return y.contiguous(memory_format=torch.channels_last)
+        y = y.contiguous(memory_format=torch.channels_last)
+        return y.half() if out_half else y
+
+    def fake_conv16(x16, w_packed16, bias=None, residual=None):       # fp16 operands, fp32 arithmetic and output
+        assert x16.dtype == torch.float16 and w_packed16.dtype == torch.float16
+        assert x16.is_contiguous(memory_format=torch.channels_last)
+        calls["conv16"] += 1
+        return fake_conv(x16.float(), w_packed16.float(), bias, residual)
 
     def fake_conv(x, w_packed, bias=None, residual=None):
         cout, cin = w_packed.shape[1], w_packed.shape[2]
@@ -675,7 +682,7 @@ def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
             y = y + residual
         return y.contiguous(memory_format=torch.channels_last)
 
-    calls = {"conv": 0, "residual": 0}
+    calls = {"conv": 0, "residual": 0, "conv16": 0}
     torch.manual_seed(0)
     vae = V.AutoencoderKL(block_out_channels=(32, 64), layers_per_block=1).eval()
     x = torch.rand(2, 3, 32, 24) * 2 - 1
@@ -696,13 +703,23 @@ def test_vae_nhwc_path_control_flow_on_cpu(monkeypatch):
             return real_fake(x, w_packed, bias, residual)
 
         monkeypatch.setattr(lib, "conv3x3_f32", counting_conv)
+        monkeypatch.setattr(lib, "conv3x3_f16in", fake_conv16)
+        monkeypatch.setattr(V, "_F16_ACT", False)
         got_mean = vae.encode(x).latent_dist.mean
         got_img = vae.decode(z).sample
-    assert calls["conv"] > 0, "the engine-convolution route was not taken"
-    assert calls["residual"] > 0, "the resnets' residual add did not ride in the convolution's epilogue"
-    assert got_mean.shape == ref_mean.shape and got_img.shape == ref_img.shape and got_img.is_contiguous()
-    assert (got_mean - ref_mean).abs().max() < 1e-4
-    assert (got_img - ref_img).abs().max() < 1e-4
+        assert calls["conv"] > 0, "the engine-convolution route was not taken"
+        assert calls["residual"] > 0, "the resnets' residual add did not ride in the convolution's epilogue"
+        assert calls["conv16"] == 0
+        assert got_mean.shape == ref_mean.shape and got_img.shape == ref_img.shape and got_img.is_contiguous()
+        assert (got_mean - ref_mean).abs().max() < 1e-4
+        assert (got_img - ref_img).abs().max() < 1e-4
+        # GroupNorm(+SiLU) -> convolution with the fp16 hand-off (64-aligned input channels only): fp16 rounding of the operands
+        monkeypatch.setattr(V, "_F16_ACT", True)
+        h_mean = vae.encode(x).latent_dist.mean
+        h_img = vae.decode(z).sample
+        assert calls["conv16"] > 0, "the fp16 hand-off was not taken"
+        assert (h_mean - ref_mean).abs().max() < 5e-3 * max(1.0, ref_mean.abs().max().item())
+        assert (h_img - ref_img).abs().max() < 5e-3 * max(1.0, ref_img.abs().max().item())
 
 
 def test_bench_emits_a_line_when_the_e2e_section_stalls():

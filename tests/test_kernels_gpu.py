@@ -592,6 +592,31 @@ def test_conv3x3_fp32_tf32(lib, B, Cin, Cout, H, W):
     assert torch.equal(lib.conv3x3_f32(x, lib.pack_conv3x3_f32(w), b, residual=res_nchw), fused)
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(1, 128, 128, 128, 96), (2, 256, 128, 64, 48), (1, 512, 512, 32, 24),
+                                            (2, 512, 256, 37, 24), (1, 128, 256, 50, 40), (3, 64, 64, 16, 8)])
+def test_conv3x3_f16_operands_fp32_out(lib, B, Cin, Cout, H, W):
+    """b200vton_conv3x3_nhwc_f16in_f32 (the VAE's GroupNorm -> convolution hand-off in fp16): on fp16-representable operands
+    the only difference from an exact fp32 convolution is the accumulation order; against the fp32 convolution of the
+    UNROUNDED operands it sits in the TF32 kernel's error class (10-bit operand mantissa). Residual epilogue bit-exact."""
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (9 * Cin) ** -0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    x16 = x.half().contiguous(memory_format=torch.channels_last)
+    w16 = lib.pack_conv3x3_f32(w).half()
+    out = lib.conv3x3_f16in(x16, w16, b)
+    assert out.shape == (B, Cout, H, W) and out.dtype == torch.float32 and out.is_contiguous(memory_format=torch.channels_last)
+    with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+        ref_rounded = torch.nn.functional.conv2d(x.half().float(), w.half().float(), b, padding=1)
+        ref = torch.nn.functional.conv2d(x, w, b, padding=1)
+    e_acc = close(out, ref_rounded, tol=2e-4)
+    e_f16 = close(out, ref, tol=2e-3)
+    e_tf32 = close(lib.conv3x3_f32(x, lib.pack_conv3x3_f32(w), b), ref, tol=2e-3)
+    print(f"fp16-operand conv vs fp32: {e_f16:.2e} (TF32 kernel {e_tf32:.2e}); vs fp32 conv of the rounded operands {e_acc:.2e}")
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    assert torch.equal(lib.conv3x3_f16in(x16, w16, b, residual=res), res + out)
+
+
 @pytest.mark.parametrize("B,C,H,W,silu", [(2, 128, 64, 48, True), (1, 256, 37, 24, True), (2, 512, 16, 12, False),
                                           (1, 128, 256, 192, True)])
 def test_groupnorm_fp32_nhwc(lib, B, C, H, W, silu):
@@ -604,6 +629,9 @@ def test_groupnorm_fp32_nhwc(lib, B, C, H, W, silu):
     ref = torch.nn.functional.silu(ref) if silu else ref
     assert out.is_contiguous(memory_format=torch.channels_last)
     close(out, ref, tol=1e-5)
+    out16 = lib.groupnorm_f32_nhwc(x, gamma, beta, 1e-6, silu, out_half=True)       # one rounding of the same fp32 values
+    assert out16.dtype == torch.float16 and out16.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out16, out.half())
 
 
 def test_vae_nhwc_route_matches_default(lib, monkeypatch):
@@ -617,9 +645,13 @@ def test_vae_nhwc_route_matches_default(lib, monkeypatch):
         monkeypatch.setattr(V, "_ENGINE_NHWC", False)
         m0, d0 = vae.encode(x).latent_dist.mean, vae.decode(z).sample
         monkeypatch.setattr(V, "_ENGINE_NHWC", True)
+        monkeypatch.setattr(V, "_F16_ACT", False)
         m1, d1 = vae.encode(x).latent_dist.mean, vae.decode(z).sample
-    close(m1, m0, tol=5e-3)
-    close(d1, d0, tol=5e-3)
+        monkeypatch.setattr(V, "_F16_ACT", True)                 # GroupNorm -> convolution hand-off in fp16 (the default)
+        m2, d2 = vae.encode(x).latent_dist.mean, vae.decode(z).sample
+    e1 = (close(m1, m0, tol=5e-3), close(d1, d0, tol=5e-3))
+    e2 = (close(m2, m0, tol=5e-3), close(d2, d0, tol=5e-3))
+    print(f"VAE vs the cuDNN route (encode mean, decode): TF32 hand-off {e1[0]:.2e} {e1[1]:.2e}, fp16 hand-off {e2[0]:.2e} {e2[1]:.2e}")
 
 
 
