@@ -20,9 +20,12 @@ def _err(a, b):
 
 @pytest.fixture(autouse=True)
 def _no_tf32():
+    """fp32 truth without TF32; the process-wide switches are restored afterwards (later test files rely on the defaults)."""
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
 
 
 # ------------------------------------------------------------------------------------------------

@@ -34,13 +34,15 @@ def _err(a, b):
 def tiny():
     from oracle import unet_ref as R
     from idm_vton_b200.engine import UNetEngine
+    prev_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)   # restored at teardown
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     cfg_t, cfg_g = R.tiny_config("tryon"), R.tiny_config("garment")
     sd_t, sd_g = _h(R.make_state_dict(cfg_t, seed=11)), _h(R.make_state_dict(cfg_g, seed=22))
     eng_t = UNetEngine(cfg_t, sd_t, "tryon")
     eng_g = UNetEngine(cfg_g, sd_g, "garment")
-    return dict(R=R, cfg_t=cfg_t, cfg_g=cfg_g, sd_t=sd_t, sd_g=sd_g, eng_t=eng_t, eng_g=eng_g)
+    yield dict(R=R, cfg_t=cfg_t, cfg_g=cfg_g, sd_t=sd_t, sd_g=sd_g, eng_t=eng_t, eng_g=eng_g)
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev_tf32
 
 
 def _engine_unets(env, x, B, h, w):

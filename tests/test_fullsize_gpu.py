@@ -53,6 +53,7 @@ def full():
     from oracle import unet_ref as R
     from idm_vton_b200 import unet as U
     from idm_vton_b200.engine import SDXL_GARMENT, SDXL_TRYON, UNetEngine
+    prev_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)   # restored at teardown
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     dev = "cuda"
@@ -66,6 +67,7 @@ def full():
     yield env
     env.clear()
     torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev_tf32
 
 
 def _forward_inputs(cfg_t, cfg_g, B, h, w, seed):

@@ -641,7 +641,8 @@ def test_vae_nhwc_route_matches_default(lib, monkeypatch):
     vae = V.AutoencoderKL().cuda().float().eval()
     x = torch.rand(1, 3, 256, 192, device="cuda") * 2 - 1
     z = torch.randn(1, 4, 32, 24, device="cuda")
-    with torch.no_grad():
+    # the route under test needs cuDNN's TF32 switch at its default (on), whatever earlier test files left behind
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=True):
         monkeypatch.setattr(V, "_ENGINE_NHWC", False)
         m0, d0 = vae.encode(x).latent_dist.mean, vae.decode(z).sample
         monkeypatch.setattr(V, "_ENGINE_NHWC", True)
