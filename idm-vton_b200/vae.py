@@ -5,9 +5,9 @@ The reference pipeline receives a diffusers `AutoencoderKL` as a component (src/
 force_upcast,latent_channels,block_out_channels}` (:911-932,1646,1868-1880). diffusers is not installable in this image, so
 this module supplies an architecture-compatible VAE (same parameter names as diffusers 0.25.0's AutoencoderKL, restated
 from its published structure) so that `__call__` runs end to end. The VAE is row (f)1 of SURVEY.md 8 ("next"): on a GPU
-the fp32 VAE runs NHWC with its 3x3 / stride-1 convolutions on `b200vton_conv3x3_nhwc_f32` (TF32 tcgen05) and every
-GroupNorm(+SiLU) on `b200vton_groupnorm_nhwc_f32` (default ON, see `_ENGINE_NHWC`), the resnets' residual add rides in the
-convolution's epilogue, the mid-block attention is a split-TF32 formulation (cuBLAS GEMMs between this library's one-pass split /
+the fp32 VAE runs NHWC with its 3x3 / stride-1 convolutions on the tcgen05 kernels `b200vton_conv3x3_nhwc_f32` (TF32
+operands) / `b200vton_conv3x3_nhwc_f16in_f32` (fp16 operands handed over by the norm: `_gn_silu_conv`) and every GroupNorm(+SiLU)
+on `b200vton_groupnorm_nhwc_f32` (default ON, see `_ENGINE_NHWC`), the resnets' residual add rides in the convolution's epilogue, the mid-block attention is a split-TF32 formulation (cuBLAS GEMMs between this library's one-pass split /
 softmax kernels); resampling and the stride-2 / 3-8-channel / 1x1 convolutions are PyTorch.
 """
 import os
