@@ -687,7 +687,7 @@ def run_b200(args, rank, world, local):
             dt = tt.item()
         e2e = {"value": n_requests * n_e2e / dt, "unit": "images/s", "h2d_bytes_per_step": h2d * len(groups),
                "d2h_bytes_per_step": d2h * len(groups), "ms_per_call": dt / n_e2e / len(groups) * 1e3,
-               "includes": "H2D, VAE encodes (masked image, pose, cloth; fp32/TF32 NHWC engine route), CLIP ViT-H image encoder "
+               "includes": "H2D, VAE encodes (masked image, pose, cloth; fp32 NHWC engine route, fp16/TF32-operand tcgen05 convolutions), CLIP ViT-H image encoder "
                "on the engine's kernels (uncond branch cached), Resampler, context K/V + hoisted garment passes, denoise loop, VAE decode, D2H of images"}
 
     guard_timer.cancel()
